@@ -1,0 +1,1195 @@
+// edm.cu — event-driven coarse time-stepper ("lift -> evolve -> restrict") for sm_100a
+// (include/b200_edm.h).
+//
+// Replaces class EventDrivenMap of the reference: host wrapper EventDrivenMap.cu:57-503 and
+// kernels EventDrivenMap.cu:378-386, 505-945.  Same map, different program:
+//
+//  reference (Kepler, FP32)                     here (B200, FP64 primary / FP32 compat)
+//  ------------------------------------------   -------------------------------------------
+//  6 launches + cuRAND + 3 H2D + memset / eval  3 launches per BATCH of evaluations
+//  LiftKernel on R*N threads (R-fold redundant) prepare kernel: once per column
+//  one thread per neuron, 1024-thread blocks    NPT neurons per thread, 128..256-thread CTAs,
+//                                               several CTAs resident per SM
+//  every neuron: pow + Newton chain per event   two-stage candidate test: a conservative
+//                                               MUFU (lg2/ex2) filter proves "cannot fire"
+//                                               for ~99% of neurons; survivors are compacted
+//                                               into one warp that runs the exact FP64
+//                                               pow + Newton (identical iterates)
+//  shuffle-tree arg-min over 1024 threads,      REDUX arg-min over the handful of candidates,
+//  2 barriers, undefined tie rule               smallest (time, index) — SURVEY Q5
+//  every thread: 3 exp per event                event-uniform exponentials computed once per
+//                                               event by the finalising thread (homogeneous
+//                                               ensemble) -> 3 FMA per neuron advance
+//  RestrictKernel on 3R*N threads for 3R items  folded into the evolve epilogue
+//  racy count + mean                            fixed-order masked mean (bitwise independent
+//                                               of how items were sharded over GPUs)
+//
+// The event sequence (which neuron fires when) is identical to the CPU restatement in
+// oracle/edm_oracle_impl.inc: the filter only ever skips neurons for which the reference's
+// `decision` predicate (EventDrivenMap.cu:559) is provably false.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "b200_edm.h"
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+// ---------------------------------------------------------------- math helpers ----
+template <typename T> struct M;
+template <> struct M<double> {
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+  static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+  static __device__ __forceinline__ double nan_() { return __longlong_as_double(0x7ff8000000000000ll); }
+};
+template <> struct M<float> {
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+  static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+  static __device__ __forceinline__ float nan_() { return __int_as_float(0x7fc00000); }
+};
+
+// model constants in the arithmetic type of the run (parameters.hpp:1-15)
+template <typename T>
+struct Consts {
+  T vth, a1, a2, b1, b2, I, L, T_end;
+  double tol;  // parameters.hpp:9: a double literal; |f| is widened for the compare
+  unsigned counter_max;
+};
+
+// counter-based standard normal (same construction as oracle_normal)
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double normal_at(unsigned long long seed, unsigned long long index) {
+  unsigned long long h1 = splitmix64(seed ^ splitmix64(2 * index));
+  unsigned long long h2 = splitmix64(seed ^ splitmix64(2 * index + 1));
+  double u1 = ((double)(h1 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  double u2 = ((double)(h2 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+// per-neuron beta ensemble; replaces curandGenerateNormal (EventDrivenMap.cu:179)
+template <typename T>
+__global__ void edm_beta_kernel(T* __restrict__ beta, size_t n, double mean, double sigma,
+                                unsigned long long seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) beta[i] = (T)(mean + sigma * normal_at(seed, i));
+}
+
+// coupling kernel w[d] = kernel at ring distance d (BuildCouplingKernel + circshift,
+// EventDrivenMap.cu:111-129, 826-841)
+template <typename T>
+__global__ void edm_coupling_kernel(Consts<T> k, unsigned N, T* __restrict__ w) {
+  unsigned d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= N) return;
+  unsigned i = (d + N / 2) % N;  // circshift by N/2
+  T x = -k.L + (T)(2 * k.L / N) * i;
+  T ax = fabs(x);
+  w[d] = (k.a1 * M<T>::exp_(-k.b1 * ax) - k.a2 * M<T>::exp_(-k.b2 * ax)) * 2 * k.L / N;
+}
+
+// ---------------------------------------------------------------- prepare (lift) ----
+// One CTA per column: initial front indices (initialSpikeInd, EventDrivenMap.cu:361-372),
+// ZtoU (:388-396) and the analytic travelling-wave profile (LiftKernel, :505-542).  The
+// lift is identical for every realisation (it uses the mean beta), so it is
+// evaluated once per column instead of once per (realisation, neuron).
+template <typename T>
+struct FrontCoef {  // x-independent factors of front m (U[m] = tau)
+  T y;                 // c * tau
+  T p1, p2;            // K+_i * exp(y (1+c b_i)/c) * exp(-b_i y)   (d > 0 branch, first two terms)
+  T q1, q2;            // K+_i * exp(-b_i y)                        (d <= 0 branch)
+  T g1, g2, e_tau;     // G_i * exp(beta tau),  exp(tau (1-beta))
+  T h1, h2, k1, k2;    // H_i * exp(b_i y),  exp(y (1 - c b_i)/c)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+edm_prepare_kernel(Consts<T> k, unsigned N, unsigned Mf, T beta, const double* __restrict__ z_cols,
+                   int32_t* __restrict__ init_index, int32_t* __restrict__ clamped,
+                   T* __restrict__ lift_v, T* __restrict__ lift_s) {
+  extern __shared__ unsigned char smem_prep[];
+  FrontCoef<T>* fc = reinterpret_cast<FrontCoef<T>*>(smem_prep);
+  const unsigned col = blockIdx.x;
+  const double* z = z_cols + (size_t)col * Mf;
+  const T one = (T)1, two = (T)2;
+  const T c = (T)z[0];
+  const T a1 = k.a1, a2 = k.a2, b1 = k.b1, b2 = k.b2, L = k.L;
+  const T cb1 = c * b1, cb2 = c * b2;
+
+  if (threadIdx.x == 0) {
+    // descending scan for the last grid point left of each front
+    int32_t prev = (int32_t)(N / 2);
+    init_index[(size_t)col * Mf] = prev;
+    int any_clamped = 0;
+    for (unsigned m = 1; m < Mf; ++m) {
+      const double target = -z[0] * z[m];
+      int32_t found = 0;
+      int hit = 0;
+      for (int32_t i = prev; i > 0; --i) {
+        if ((double)(-L + (T)(2 * (unsigned)i * L / N)) < target) { found = i; hit = 1; break; }
+      }
+      if (!hit) any_clamped = 1;  // front outside the domain -> index 0 + soft flag
+      init_index[(size_t)col * Mf + m] = found;
+      prev = found;
+    }
+    if (any_clamped) atomicOr(clamped, 1);
+  }
+  // x-independent coefficients, one thread per front
+  for (unsigned m = threadIdx.x; m < Mf; m += blockDim.x) {
+    const T tau = (m == 0) ? (T)0 : (T)z[m];  // U = (c, 0, T_2, ..., T_M)
+    const T y = c * tau;
+    FrontCoef<T> f;
+    f.y = y;
+    const T Kp1 = (a1 * beta * c) / ((beta + cb1) * (one + cb1));
+    const T Kp2 = (a2 * beta * c) / ((beta + cb2) * (one + cb2));
+    f.q1 = Kp1 * M<T>::exp_(-b1 * y);
+    f.q2 = Kp2 * M<T>::exp_(-b2 * y);
+    f.p1 = Kp1 * M<T>::exp_(y * ((one + cb1) / c)) * M<T>::exp_(-b1 * y);
+    f.p2 = Kp2 * M<T>::exp_(y * ((one + cb2) / c)) * M<T>::exp_(-b2 * y);
+    f.g1 = (a1 * beta * c / (one - beta)) * M<T>::exp_(beta * tau) * (one / (beta + cb1) + one / (cb1 - beta));
+    f.g2 = (a2 * beta * c / (one - beta)) * M<T>::exp_(beta * tau) * (one / (beta + cb2) + one / (cb2 - beta));
+    f.e_tau = M<T>::exp_(tau * (one - beta));
+    f.h1 = (a1 * beta * c / ((cb1 - beta) * (one - cb1))) * M<T>::exp_(b1 * y);
+    f.h2 = (a2 * beta * c / ((cb2 - beta) * (one - cb2))) * M<T>::exp_(b2 * y);
+    f.k1 = M<T>::exp_(y * ((one - cb1) / c));
+    f.k2 = M<T>::exp_(y * ((one - cb2) / c));
+    fc[m] = f;
+  }
+  __syncthreads();
+
+  // synaptic-profile constants of the "behind the front" branch
+  const T s_a1 = beta * a1 * (c / (beta + cb1)), s_a2 = beta * a2 * (c / (beta + cb2));
+  const T s_c1 = (two * a1 / b1) * (beta / (one - ((beta * beta) / (c * c * b1 * b1))));
+  const T s_c2 = (two * a2 / b2) * (beta / (one - ((beta * beta) / (c * c * b2 * b2))));
+  const T s_d1 = beta * a1 * (c / (cb1 - beta)), s_d2 = beta * a2 * (c / (cb2 - beta));
+
+  for (unsigned j = threadIdx.x; j < N; j += blockDim.x) {
+    const T x = L - (T)(2 * L / N) * j;
+    // factors that depend on x only
+    const T ex_beta = M<T>::exp_((x / c) * (one - beta));
+    const T ex_m1 = M<T>::exp_(x * ((one - cb1) / c)), ex_m2 = M<T>::exp_(x * ((one - cb2) / c));
+    const T ex_p1 = M<T>::exp_(x * ((one + cb1) / c)), ex_p2 = M<T>::exp_(x * ((one + cb2) / c));
+    const T ex_lead = M<T>::exp_(-x / c);
+    T acc_v = (T)0, acc_s = (T)0;
+    for (unsigned m = 0; m < Mf; ++m) {
+      const FrontCoef<T> f = fc[m];
+      const T d = x - f.y;
+      // both branches are evaluated and multiplied by 0/1 masks exactly as the reference
+      // does, so overflow-to-NaN behaviour is preserved
+      const T gt = (T)(d > (T)0), le = (T)(d <= (T)0);
+      const T ahead = f.p1 - f.p2 + f.g1 * (ex_beta - f.e_tau) - f.h1 * (ex_m1 - f.k1)
+                      - f.g2 * (ex_beta - f.e_tau) + f.h2 * (ex_m2 - f.k2);
+      const T behind = f.q1 * ex_p1 - f.q2 * ex_p2;
+      const T dv = (gt * ahead + le * behind) * ex_lead;
+      acc_v += dv - gt * M<T>::exp_(-d / c) + le * (T)0;
+      const T e = f.y - x;  // = -d
+      const T gt2 = (T)(e > (T)0), le2 = (T)(e <= (T)0);
+      acc_s += gt2 * (s_a1 * M<T>::exp_(b1 * (x - f.y)) - s_a2 * M<T>::exp_(b2 * (x - f.y)))
+             + le2 * (s_c1 * M<T>::exp_(-(beta / c) * (x - f.y)) - s_d1 * M<T>::exp_(b1 * (f.y - x))
+                      - s_c2 * M<T>::exp_(-(beta / c) * (x - f.y)) + s_d2 * M<T>::exp_(b2 * (f.y - x)));
+    }
+    T v = k.I + acc_v;
+    v *= (T)(v < one);  // neurons lifted above threshold start from reset
+    lift_v[(size_t)col * N + j] = v;
+    lift_s[(size_t)col * N + j] = acc_s;
+  }
+}
+
+// ---------------------------------------------------------------- evolve ----
+// Exact event time of one neuron: `decision` predicate + Newton from t = 0
+// (eventTime/fun/dfun, EventDrivenMap.cu:544-573).  Returns 100 when the neuron cannot fire.
+template <typename T>
+__device__ __forceinline__ T exact_event_time(const Consts<T>& k, T v, T s, T beta, unsigned& its) {
+  const T one = (T)1;
+  const T r = s / (k.vth - k.I);
+  const T p = M<T>::pow_(r, one / beta);
+  const bool decision = v > k.vth * p + k.I * (one - p) - (k.vth - k.I) / (beta - one) * (r - p);
+  if (!decision) return (T)100;
+  T t = (T)0;
+  T f = v - k.vth;         // fun(0)  : exp(0) = 1 makes every other term exactly 0
+  T df = (k.I - v) + s;    // dfun(0)
+  unsigned counter = 0;
+  while (((double)fabs(f) > k.tol) && (counter < k.counter_max)) {
+    t -= f / df;
+    const T e1 = M<T>::exp_(-t);
+    const T e2 = M<T>::exp_((one - beta) * t);
+    f = v * e1 + k.I * (one - e1) + s * e1 / (one - beta) * (e2 - one) - k.vth;
+    df = k.I * e1 - v * e1 + s * e1 * e2 + (s * e1 * (e2 - one)) / (beta - one);
+    counter++;
+  }
+  its += counter;
+  T out = fabs(t);
+  if (out != out) out = (T)100;  // Q5: a NaN event time never wins the arg-min
+  return out;
+}
+
+// order-preserving integer key of a non-negative, non-NaN time
+__device__ __forceinline__ unsigned long long time_key(double t) { return (unsigned long long)__double_as_longlong(t); }
+__device__ __forceinline__ unsigned long long time_key(float t) { return (unsigned long long)__float_as_uint(t); }
+
+// warp-wide lexicographic min of (key, idx); every lane gets the result
+__device__ __forceinline__ void warp_argmin(unsigned long long& key, unsigned& idx) {
+  const unsigned full = 0xffffffffu;
+  unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  unsigned mhi = __reduce_min_sync(full, hi);
+  unsigned lo_c = (hi == mhi) ? lo : 0xffffffffu;
+  unsigned mlo = __reduce_min_sync(full, lo_c);
+  unsigned id_c = (hi == mhi && lo == mlo) ? idx : 0xffffffffu;
+  idx = __reduce_min_sync(full, id_c);
+  key = ((unsigned long long)mhi << 32) | mlo;
+}
+
+template <typename T>
+struct EventMsg {       // written by the finalising thread, read by everybody after the barrier
+  T dt, e1, cA, cB, e12;  // event-uniform advance coefficients (cB, e12: homogeneous ensemble)
+  unsigned idx;
+  int cont;             // 1: advance and continue, 0: stop
+  int fallback;         // 1: nobody can fire within 100 time units -> block-wide exact pass
+};
+
+template <typename T>
+struct EvolveArgs {
+  Consts<T> k;
+  unsigned N, R, Mf;
+  T beta_mean;
+  const T* beta;        // [R][N] or nullptr (homogeneous)
+  const T* w;           // [N]
+  const T* lift_v;      // [ncols][N]
+  const T* lift_s;
+  const int32_t* init_index;  // [ncols][M]
+  unsigned long long item_begin;
+  // outputs, indexed by local item (blockIdx.x)
+  T* position;          // [items][M]
+  int32_t* accept;      // [items]
+  int32_t* event_count; // [items]
+  int32_t* last_index;  // [items][M]   (nullable group: debug)
+  int32_t* crossed_index;
+  T* last_time;
+  T* crossed_time;
+  unsigned long long* counters;  // [4]: events, candidates (filter survivors), newton its, fallbacks (nullable)
+};
+
+template <typename T>
+__host__ __device__ inline size_t evolve_smem_bytes(unsigned N, unsigned Mf, bool het) {
+  size_t b = 0;
+  b += sizeof(T) * N;                       // bw / w
+  b += sizeof(T) * N * (het ? 3 : 2);       // cand_v, cand_s, (cand_b)
+  b += sizeof(int) * N;                     // cand_i
+  b += (sizeof(T) * 2 + sizeof(int) * 2 + 4) * Mf;  // front bookkeeping
+  b += 256;                                 // scalars + alignment slack
+  b += 32 * 16;                             // per-warp partial results
+  return b;
+}
+
+template <typename T, int NPT, bool HET, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+edm_evolve_kernel(const EvolveArgs<T> A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned N = A.N, Mf = A.Mf;
+  const unsigned tid = threadIdx.x, nthr = blockDim.x;
+  const unsigned lane = tid & 31, warp = tid >> 5, nwarps = (nthr + 31) >> 5;
+  // ---- shared memory carve-up ----
+  unsigned char* sp = smem_raw;
+  T* bw = reinterpret_cast<T*>(sp); sp += sizeof(T) * N;            // w[d] (x beta when homogeneous)
+  T* cand_v = reinterpret_cast<T*>(sp); sp += sizeof(T) * N;
+  T* cand_s = reinterpret_cast<T*>(sp); sp += sizeof(T) * N;
+  T* cand_b = nullptr;
+  if (HET) { cand_b = reinterpret_cast<T*>(sp); sp += sizeof(T) * N; }
+  T* last_t = reinterpret_cast<T*>(sp); sp += sizeof(T) * Mf;
+  T* cross_t = reinterpret_cast<T*>(sp); sp += sizeof(T) * Mf;
+  sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
+  unsigned long long* wkey = reinterpret_cast<unsigned long long*>(sp); sp += 8 * 32;
+  EventMsg<T>* ev = reinterpret_cast<EventMsg<T>*>(sp); sp += ((sizeof(EventMsg<T>) + 15) / 16) * 16;
+  unsigned long long* fb_key = reinterpret_cast<unsigned long long*>(sp); sp += 8;
+  int* cand_i = reinterpret_cast<int*>(sp); sp += sizeof(int) * N;
+  int* last_i = reinterpret_cast<int*>(sp); sp += sizeof(int) * Mf;
+  int* cross_i = reinterpret_cast<int*>(sp); sp += sizeof(int) * Mf;
+  unsigned* widx = reinterpret_cast<unsigned*>(sp); sp += 4 * 32;
+  int* ncand = reinterpret_cast<int*>(sp); sp += 8;                 // [2], double buffered
+  unsigned* fb_idx = reinterpret_cast<unsigned*>(sp); sp += 4;
+  unsigned char* crossed = sp;                                      // [Mf]
+
+  const unsigned long long item = A.item_begin + blockIdx.x;
+  const unsigned col = (unsigned)(item / A.R), r = (unsigned)(item % A.R);
+  const Consts<T> k = A.k;
+  const T one = (T)1;
+
+  // ---- per-neuron state in registers; neuron j = tid + q * nthr ----
+  T v[NPT], s[NPT], bt[HET ? NPT : 1], ibm1[HET ? NPT : 1];
+  bool filt[HET ? NPT : 1];
+#pragma unroll
+  for (int q = 0; q < NPT; ++q) {
+    const unsigned j = tid + q * nthr;
+    if (j < N) {
+      v[q] = A.lift_v[(size_t)col * N + j];
+      s[q] = A.lift_s[(size_t)col * N + j];
+      if (HET) {
+        bt[q] = A.beta[(size_t)r * N + j];
+        ibm1[q] = one / (bt[q] - one);
+        filt[q] = bt[q] >= (T)1.5;
+      }
+    } else {
+      v[q] = (T)0; s[q] = (T)0;
+      if (HET) { bt[q] = (T)2; ibm1[q] = one; filt[q] = true; }
+    }
+  }
+  // homogeneous-ensemble constants
+  const T hb = A.beta_mean;
+  const T h_ibm1 = one / (hb - one);
+  const T h_i1mb = one / (one - hb);
+  const bool h_filt = hb >= (T)1.5;
+  const T inv_vmI = one / (k.vth - k.I);
+  const T vmI = k.vth - k.I;
+
+  for (unsigned d = tid; d < N; d += nthr) bw[d] = HET ? A.w[d] : hb * A.w[d];
+  if (tid == 0) {
+    ncand[0] = 0; ncand[1] = 0;
+    for (unsigned m = 0; m < Mf; ++m) {
+      last_i[m] = A.init_index[(size_t)col * Mf + m];  // EventDrivenMap.cu:595-599
+      last_t[m] = (T)0;                                // Q4
+      cross_i[m] = 0; cross_t[m] = (T)0; crossed[m] = 0;
+    }
+  }
+  // finalising-thread state
+  T t_now = (T)0;
+  unsigned n_crossed = 0;
+  int n_events = 0;
+  unsigned stat_cand = 0, stat_newton = 0, stat_fb = 0;
+  __syncthreads();
+
+  // Conservative candidate test.  The reference's predicate is
+  //   v > vth p + I (1-p) - (vth-I)/(beta-1) (r - p),  r = s/(vth-I), p = r^(1/beta),
+  // i.e. g := (v - vth) - (vth-I) * ((beta p - r)/(beta-1) - 1) > 0.  p is evaluated with the
+  // MUFU lg2/ex2 units (relative error < 2e-6); the neuron is dropped only when g is below
+  // -1e-4 (1 + p), orders of magnitude more than that error can move it.
+  auto scan = [&](int parity) {
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) {
+      const unsigned j = tid + q * nthr;
+      if (j >= N) continue;
+      const T b = HET ? bt[q] : hb;
+      const bool fo = HET ? filt[q] : h_filt;
+      const T rr = s[q] * inv_vmI;
+      bool maybe;
+      if (!fo) maybe = true;
+      else if (rr > (T)0) {
+        if (rr > (T)1e-30 && rr < (T)1e30) {
+          const float p32 = exp2f(__log2f((float)rr) * (float)(one / b));
+          const T p = (T)p32;
+          const T g = (v[q] - k.vth) - vmI * ((b * p - rr) * (HET ? ibm1[q] : h_ibm1) - one);
+          maybe = !(g < (T)-1e-4 * (one + p));
+        } else maybe = true;
+      } else maybe = (rr == (T)0);  // r < 0 or NaN: pow() is NaN, the predicate is false
+      if (maybe) {
+        const int slot = atomicAdd(&ncand[parity], 1);
+        cand_v[slot] = v[q]; cand_s[slot] = s[q]; cand_i[slot] = (int)j;
+        if (HET) cand_b[slot] = b;
+      }
+    }
+  };
+
+  // Bookkeeping of one event by the finalising thread (EventDrivenMap.cu:620-643) and the
+  // event-uniform advance coefficients for everybody else.
+  auto finalise = [&](T dt, unsigned idx) {
+    t_now += dt;
+    n_events++;
+    unsigned mi = 0;
+    for (unsigned i = 1; i < Mf; ++i) {  // literal `minIndex += (closer)` — SURVEY Q14
+      const int di = abs((int)idx - last_i[i]);
+      const int dm = abs((int)idx - last_i[mi]);
+      mi += (unsigned)(di < dm);
+    }
+    if (!crossed[mi]) {
+      if (t_now > k.T_end) { cross_t[mi] = t_now; cross_i[mi] = (int)idx; crossed[mi] = 1; n_crossed++; }
+      else { last_t[mi] = t_now; last_i[mi] = (int)idx; }
+    }
+    const int cont = (n_crossed < Mf) && (t_now < 2 * k.T_end);  // :601
+    EventMsg<T> m;
+    m.dt = dt; m.idx = idx; m.cont = cont; m.fallback = 0;
+    m.e1 = m.cA = m.cB = m.e12 = (T)0;
+    if (cont) {
+      const T e1 = M<T>::exp_(-dt);
+      m.e1 = e1;
+      m.cA = k.I * (one - e1);
+      if (!HET) {
+        const T e2 = M<T>::exp_((one - hb) * dt);
+        m.cB = e1 * h_i1mb * (e2 - one);
+        m.e12 = e1 * e2;
+      }
+    }
+    *ev = m;
+  };
+
+  int parity = 0;
+  scan(parity);
+  for (;;) {
+    __syncthreads();  // B1: candidate list of this event is complete
+    const int n = ncand[parity];
+    if (tid == 0) ncand[parity ^ 1] = 0;
+    // ---- exact event times of the candidates, compacted into the first warps ----
+    const unsigned long long kInf = ~0ull;
+    unsigned long long key = kInf;
+    unsigned bidx = 0xffffffffu;
+    for (int c = (int)tid; c < n; c += (int)nthr) {
+      unsigned its = 0;
+      const T tc = exact_event_time<T>(k, cand_v[c], cand_s[c], HET ? cand_b[c] : hb, its);
+      if (A.counters) stat_newton += its;
+      const unsigned long long kc = time_key(tc);
+      const unsigned ic = (unsigned)cand_i[c];
+      if (kc < key || (kc == key && ic < bidx)) { key = kc; bidx = ic; }
+    }
+    const bool multi = n > 32;  // block-uniform
+    if (warp == 0 || (multi && warp * 32 < (unsigned)n)) warp_argmin(key, bidx);
+    if (multi) {
+      if (lane == 0) { wkey[warp] = (warp * 32 < (unsigned)n) ? key : kInf; widx[warp] = bidx; }
+      __syncthreads();
+      if (warp == 0) {
+        key = (lane < nwarps) ? wkey[lane] : kInf;
+        bidx = (lane < nwarps) ? widx[lane] : 0xffffffffu;
+        warp_argmin(key, bidx);
+      }
+    }
+    if (tid == 0) {
+      if (A.counters) stat_cand += (unsigned)n;
+      // all non-candidates sit at exactly 100: if no candidate beats that, the winner is
+      // the smallest-index neuron at 100 and must be found by the exact block-wide pass
+      if (n == 0 || key >= time_key((T)100)) {
+        EventMsg<T> m;
+        m.dt = m.e1 = m.cA = m.cB = m.e12 = (T)0; m.idx = 0; m.cont = 1; m.fallback = 1;
+        *ev = m;
+        *fb_key = kInf; *fb_idx = 0xffffffffu;
+        stat_fb++;
+      } else {
+        T dt;
+        if (sizeof(T) == 8) dt = (T)__longlong_as_double((long long)key);
+        else dt = (T)__uint_as_float((unsigned)key);
+        finalise(dt, bidx);
+      }
+    }
+    __syncthreads();  // B2: event message visible
+    if (ev->fallback) {
+      // exact pass over every neuron (rare: the ring has gone quiet)
+      unsigned long long mk = kInf;
+      unsigned long long keys[NPT];
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) {
+        const unsigned j = tid + q * nthr;
+        keys[q] = kInf;
+        if (j < N) {
+          unsigned its = 0;
+          keys[q] = time_key(exact_event_time<T>(k, v[q], s[q], HET ? bt[q] : hb, its));
+          if (keys[q] < mk) mk = keys[q];
+        }
+      }
+      atomicMin(fb_key, mk);
+      __syncthreads();
+      const unsigned long long gk = *fb_key;
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) {
+        const unsigned j = tid + q * nthr;
+        if (j < N && keys[q] == gk) atomicMin(fb_idx, j);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        T dt;
+        if (sizeof(T) == 8) dt = (T)__longlong_as_double((long long)gk);
+        else dt = (T)__uint_as_float((unsigned)gk);
+        finalise(dt, *fb_idx);
+      }
+      __syncthreads();
+    }
+    const EventMsg<T> m = *ev;
+    if (!m.cont) break;
+    // ---- advance every neuron to the event, reset the firing one, deliver the kick
+    //      (EventDrivenMap.cu:612-618), then test who can fire next ----
+    parity ^= 1;
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) {
+      const unsigned j = tid + q * nthr;
+      if (j >= N) continue;
+      const unsigned dist = (j >= m.idx) ? (j - m.idx) : (m.idx - j);
+      if (HET) {
+        const T b = bt[q];
+        const T e2 = M<T>::exp_((one - b) * m.dt);
+        const T cB = m.e1 * (-ibm1[q]) * (e2 - one);
+        T vn = v[q] * m.e1 + (m.cA + s[q] * cB);
+        v[q] = (j == m.idx) ? (T)0 : vn;
+        s[q] = s[q] * (m.e1 * e2) + b * bw[dist];
+      } else {
+        T vn = v[q] * m.e1 + (m.cA + s[q] * m.cB);
+        v[q] = (j == m.idx) ? (T)0 : vn;
+        s[q] = s[q] * m.e12 + bw[dist];
+      }
+    }
+    scan(parity);
+  }
+
+  // ---- epilogue: restriction by two-point linear interpolation in time
+  //      (RestrictKernel, EventDrivenMap.cu:769-785) and the accept flag (:669-672) ----
+  if (tid == 0) {
+    const size_t o = (size_t)blockIdx.x;
+    for (unsigned m = 0; m < Mf; ++m) {
+      const T t0 = last_t[m], t1 = cross_t[m];
+      const T x0 = -k.L + (T)2 * k.L / N * last_i[m];
+      const T x1 = -k.L + (T)2 * k.L / N * cross_i[m];
+      A.position[o * Mf + m] = x0 + (k.T_end - t0) * (x1 - x0) / (t1 - t0);
+      if (A.last_index) {
+        A.last_index[o * Mf + m] = last_i[m];
+        A.crossed_index[o * Mf + m] = cross_i[m];
+        A.last_time[o * Mf + m] = t0;
+        A.crossed_time[o * Mf + m] = t1;
+      }
+    }
+    A.accept[o] = (n_crossed == Mf) ? 1 : 0;
+    A.event_count[o] = n_events;
+    if (A.counters) {
+      atomicAdd(&A.counters[0], (unsigned long long)n_events);
+      atomicAdd(&A.counters[1], (unsigned long long)stat_cand);
+      atomicAdd(&A.counters[3], (unsigned long long)stat_fb);
+    }
+  }
+  if (A.counters) {
+    // Newton iterations were counted by whichever thread ran them
+    unsigned tot = stat_newton;
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, off);
+    if (lane == 0 && tot) atomicAdd(&A.counters[2], (unsigned long long)tot);
+  }
+}
+
+// ---------------------------------------------------------------- reduce ----
+// Masked mean over realisations in a FIXED order (CountRealisationsKernel +
+// realisationReductionKernelBlocks, EventDrivenMap.cu:787-824) and the residual
+// F = -c U[1..M] - X_T + c T (EventDrivenMap.cu:239).  One CTA per column.
+template <typename T>
+__global__ void __launch_bounds__(256)
+edm_reduce_kernel(unsigned R, unsigned Mf, double T_end, unsigned quirks,
+                  const double* __restrict__ z_cols, const T* __restrict__ position,
+                  const int32_t* __restrict__ accept, double* __restrict__ f_cols,
+                  double* __restrict__ mean_cols) {
+  __shared__ T part[256];
+  __shared__ unsigned cnt_part[256];
+  __shared__ unsigned s_count;
+  const unsigned col = blockIdx.x, tid = threadIdx.x;
+  const T* pos = position + (size_t)col * R * Mf;
+  const int32_t* acc = accept + (size_t)col * R;
+  unsigned c = 0;
+  for (unsigned rr = tid; rr < R; rr += 256) c += (unsigned)(acc[rr] == 1);
+  cnt_part[tid] = c;
+  __syncthreads();
+  for (unsigned o = 128; o > 0; o >>= 1) {
+    if (tid < o) cnt_part[tid] += cnt_part[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) s_count = cnt_part[0];
+  __syncthreads();
+  const unsigned count = s_count;
+  const double* z = z_cols + (size_t)col * Mf;
+  for (unsigned m = 0; m < Mf; ++m) {
+    T sum = (T)0;
+    for (unsigned rr = tid; rr < R; rr += 256) {
+      bool take = acc[rr] == 1;
+      if ((quirks & B200_EDM_QUIRK_ACCEPT0_BIAS) && rr == 0) take = (count == 1);
+      if (take) sum += pos[(size_t)rr * Mf + m];
+    }
+    part[tid] = sum;
+    __syncthreads();
+    for (unsigned o = 128; o > 0; o >>= 1) {
+      if (tid < o) part[tid] += part[tid + o];
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const T mean = part[0] / count;
+      const double Um = (m == 0) ? 0.0 : z[m];
+      f_cols[(size_t)col * Mf + m] = (-z[0]) * Um - (double)mean + z[0] * T_end;
+      if (mean_cols) mean_cols[(size_t)col * Mf + m] = (double)mean;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, typename U>
+__global__ void convert_kernel(const T* __restrict__ in, U* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (U)in[i];
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+// ---------------------------------------------------------------- handle ----
+struct b200_edm {
+  std::vector<double> params;
+  b200_edm_model model;
+  uint32_t R, N, Mf;
+  b200_dtype prec;
+  double sigma = 0.0;
+  uint64_t seed = 42;
+  int debug = 0, timing = 0, npt = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_up = nullptr;
+  bool up_pending = false;
+  // ensemble-level device state
+  void* w = nullptr;
+  void* beta = nullptr;
+  bool w_dirty = true, beta_dirty = true;
+  // batch-level device state (capacity in columns / items)
+  size_t cap_cols = 0, cap_items = 0;
+  double* d_z = nullptr;
+  double* d_f = nullptr;
+  double* d_mean = nullptr;
+  int32_t* d_init = nullptr;
+  int32_t* d_clamped = nullptr;
+  void* d_lv = nullptr;
+  void* d_ls = nullptr;
+  void* d_pos = nullptr;
+  int32_t* d_accept = nullptr;
+  int32_t* d_evcount = nullptr;
+  int32_t* d_last_i = nullptr;
+  int32_t* d_cross_i = nullptr;
+  void* d_last_t = nullptr;
+  void* d_cross_t = nullptr;
+  unsigned long long* d_counters = nullptr;
+  double* h_pin = nullptr;  // pinned staging for z in / f out
+  size_t h_pin_cap = 0;
+  // last call
+  size_t last_cols = 0;
+  double last_ms = 0.0;
+  unsigned long long last_counters[4] = {0, 0, 0, 0};
+  int last_clamped = 0;
+  char err[256] = "";
+};
+
+namespace {
+
+size_t esize(const b200_edm* h) { return h->prec == B200_F64 ? 8 : 4; }
+
+template <typename T>
+Consts<T> make_consts(const b200_edm* h) {
+  Consts<T> k;
+  k.vth = (T)h->model.vth; k.a1 = (T)h->model.a1; k.a2 = (T)h->model.a2;
+  k.b1 = (T)h->model.b1; k.b2 = (T)h->model.b2; k.I = (T)h->model.I; k.L = (T)h->model.L;
+  k.T_end = (T)h->model.time_horizon; k.tol = h->model.tol; k.counter_max = h->model.counter_max;
+  return k;
+}
+
+void free_ensemble(b200_edm* h) {
+  cudaFree(h->w); cudaFree(h->beta);
+  h->w = h->beta = nullptr;
+  h->w_dirty = h->beta_dirty = true;
+}
+void free_batch(b200_edm* h) {
+  cudaFree(h->d_z); cudaFree(h->d_f); cudaFree(h->d_mean); cudaFree(h->d_init); cudaFree(h->d_lv);
+  cudaFree(h->d_ls); cudaFree(h->d_pos); cudaFree(h->d_accept); cudaFree(h->d_evcount);
+  cudaFree(h->d_last_i); cudaFree(h->d_cross_i); cudaFree(h->d_last_t); cudaFree(h->d_cross_t);
+  h->d_z = h->d_f = h->d_mean = nullptr; h->d_init = nullptr; h->d_lv = h->d_ls = h->d_pos = nullptr;
+  h->d_accept = h->d_evcount = h->d_last_i = h->d_cross_i = nullptr; h->d_last_t = h->d_cross_t = nullptr;
+  h->cap_cols = h->cap_items = 0;
+}
+
+int ensure_pinned(b200_edm* h, size_t doubles) {
+  if (doubles <= h->h_pin_cap) return B200_OK;
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  h->h_pin = nullptr; h->h_pin_cap = 0;
+  B200_CUDA(cudaHostAlloc((void**)&h->h_pin, doubles * sizeof(double), cudaHostAllocDefault));
+  h->h_pin_cap = doubles;
+  return B200_OK;
+}
+
+int ensure_batch(b200_edm* h, size_t ncols, size_t nitems) {
+  const size_t es = esize(h), N = h->N, Mf = h->Mf;
+  if (ncols > h->cap_cols) {
+    cudaFree(h->d_z); cudaFree(h->d_f); cudaFree(h->d_mean); cudaFree(h->d_init); cudaFree(h->d_lv); cudaFree(h->d_ls);
+    h->d_z = h->d_f = h->d_mean = nullptr; h->d_init = nullptr; h->d_lv = h->d_ls = nullptr; h->cap_cols = 0;
+    B200_CUDA(cudaMalloc(&h->d_z, ncols * Mf * sizeof(double)));
+    B200_CUDA(cudaMalloc(&h->d_f, ncols * Mf * sizeof(double)));
+    B200_CUDA(cudaMalloc(&h->d_mean, ncols * Mf * sizeof(double)));
+    B200_CUDA(cudaMalloc(&h->d_init, ncols * Mf * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&h->d_lv, ncols * N * es));
+    B200_CUDA(cudaMalloc(&h->d_ls, ncols * N * es));
+    h->cap_cols = ncols;
+  }
+  if (nitems > h->cap_items) {
+    cudaFree(h->d_pos); cudaFree(h->d_accept); cudaFree(h->d_evcount); cudaFree(h->d_last_i);
+    cudaFree(h->d_cross_i); cudaFree(h->d_last_t); cudaFree(h->d_cross_t);
+    h->d_pos = nullptr; h->d_accept = h->d_evcount = h->d_last_i = h->d_cross_i = nullptr;
+    h->d_last_t = h->d_cross_t = nullptr; h->cap_items = 0;
+    B200_CUDA(cudaMalloc(&h->d_pos, nitems * Mf * es));
+    B200_CUDA(cudaMalloc(&h->d_accept, nitems * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&h->d_evcount, nitems * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&h->d_last_i, nitems * Mf * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&h->d_cross_i, nitems * Mf * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&h->d_last_t, nitems * Mf * es));
+    B200_CUDA(cudaMalloc(&h->d_cross_t, nitems * Mf * es));
+    h->cap_items = nitems;
+  }
+  if (!h->d_clamped) B200_CUDA(cudaMalloc(&h->d_clamped, sizeof(int32_t)));
+  if (!h->d_counters) B200_CUDA(cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
+  return B200_OK;
+}
+
+// (re)build the coupling kernel and the beta ensemble when their inputs changed
+template <typename T>
+int ensure_ensemble(b200_edm* h, cudaStream_t st) {
+  if (h->w_dirty) {
+    cudaFree(h->w); h->w = nullptr;
+    B200_CUDA(cudaMalloc(&h->w, (size_t)h->N * sizeof(T)));
+    edm_coupling_kernel<T><<<(h->N + 255) / 256, 256, 0, st>>>(make_consts<T>(h), h->N, (T*)h->w);
+    B200_CUDA(cudaGetLastError());
+    h->w_dirty = false;
+  }
+  if (h->sigma != 0.0) {
+    if (h->beta_dirty) {
+      cudaFree(h->beta); h->beta = nullptr;
+      const size_t n = (size_t)h->R * h->N;
+      B200_CUDA(cudaMalloc(&h->beta, n * sizeof(T)));
+      edm_beta_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((T*)h->beta, n, h->params[0], h->sigma, h->seed);
+      B200_CUDA(cudaGetLastError());
+      h->beta_dirty = false;
+    }
+  }
+  return B200_OK;
+}
+
+int pick_npt(const b200_edm* h) {
+  if (h->npt > 0) return h->npt;
+  const unsigned N = h->N;
+  if (N <= 128) return 1;
+  if (N <= 256) return 2;
+  if (N <= 512) return 4;
+  if (N <= 2048) return 8;
+  return 16;
+}
+
+template <typename T, int NPT, bool HET>
+int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaStream_t st) {
+  unsigned threads = (h->N + NPT - 1) / NPT;
+  threads = (threads + 31) / 32 * 32;
+  if (threads > 1024) return fail(B200_ERR_UNSUPPORTED, "no_neurons=%u needs more than 1024 threads at %d neurons/thread", h->N, NPT);
+  const size_t smem = evolve_smem_bytes<T>(h->N, h->Mf, HET);
+  if (smem > 227 * 1024) return fail(B200_ERR_UNSUPPORTED, "no_neurons=%u / no_fronts=%u need %zu B of shared memory (max 232448)", h->N, h->Mf, smem);
+  if (threads <= 256) {
+    auto kern = edm_evolve_kernel<T, NPT, HET, 256>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nitems, threads, smem, st>>>(A);
+  } else {
+    auto kern = edm_evolve_kernel<T, NPT, HET, 1024>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nitems, threads, smem, st>>>(A);
+  }
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+template <typename T, bool HET>
+int launch_evolve(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaStream_t st) {
+  switch (pick_npt(h)) {
+    case 1: return launch_evolve_npt<T, 1, HET>(h, A, nitems, st);
+    case 2: return launch_evolve_npt<T, 2, HET>(h, A, nitems, st);
+    case 4: return launch_evolve_npt<T, 4, HET>(h, A, nitems, st);
+    case 8: return launch_evolve_npt<T, 8, HET>(h, A, nitems, st);
+    case 16: return launch_evolve_npt<T, 16, HET>(h, A, nitems, st);
+    default: return fail(B200_ERR_INVALID_ARG, "neurons per thread must be 1, 2, 4, 8 or 16");
+  }
+}
+
+// prepare (lift) for ncols columns whose z already sits in h->d_z
+template <typename T>
+int run_prepare(b200_edm* h, size_t ncols, cudaStream_t st) {
+  B200_CUDA(cudaMemsetAsync(h->d_clamped, 0, sizeof(int32_t), st));
+  const size_t smem = sizeof(FrontCoef<T>) * h->Mf;
+  if (smem > 200 * 1024) return fail(B200_ERR_UNSUPPORTED, "no_fronts=%u too large for the lift kernel", h->Mf);
+  auto kern = edm_prepare_kernel<T>;
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)ncols, 256, smem, st>>>(make_consts<T>(h), h->N, h->Mf, (T)h->params[0], h->d_z,
+                                           h->d_init, h->d_clamped, (T*)h->d_lv, (T*)h->d_ls);
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// evolve items [item_begin, item_end) into pos/accept (local item order)
+template <typename T>
+int run_evolve(b200_edm* h, size_t item_begin, size_t item_end, T* pos, int32_t* accept, cudaStream_t st) {
+  EvolveArgs<T> A;
+  A.k = make_consts<T>(h);
+  A.N = h->N; A.R = h->R; A.Mf = h->Mf;
+  A.beta_mean = (T)h->params[0];
+  A.beta = (h->sigma != 0.0) ? (const T*)h->beta : nullptr;
+  A.w = (const T*)h->w;
+  A.lift_v = (const T*)h->d_lv; A.lift_s = (const T*)h->d_ls;
+  A.init_index = h->d_init;
+  A.item_begin = item_begin;
+  A.position = pos; A.accept = accept; A.event_count = h->d_evcount;
+  A.last_index = h->d_last_i; A.crossed_index = h->d_cross_i;
+  A.last_time = (T*)h->d_last_t; A.crossed_time = (T*)h->d_cross_t;
+  A.counters = (h->debug || h->timing) ? h->d_counters : nullptr;
+  const size_t nitems = item_end - item_begin;
+  if (nitems == 0) return B200_OK;
+  if (nitems > 0x7fffffffull) return fail(B200_ERR_UNSUPPORTED, "too many work items in one launch");
+  if (A.counters) B200_CUDA(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  if (h->timing) B200_CUDA(cudaEventRecord(h->ev0, st));
+  int rc = (h->sigma != 0.0) ? launch_evolve<T, true>(h, A, nitems, st) : launch_evolve<T, false>(h, A, nitems, st);
+  if (rc != B200_OK) return rc;
+  if (h->timing) B200_CUDA(cudaEventRecord(h->ev1, st));
+  return B200_OK;
+}
+
+template <typename T>
+int run_reduce(b200_edm* h, size_t ncols, const T* pos, const int32_t* accept, double* f_cols, cudaStream_t st) {
+  edm_reduce_kernel<T><<<(unsigned)ncols, 256, 0, st>>>(h->R, h->Mf, (double)(T)h->model.time_horizon,
+                                                        h->model.quirks, h->d_z, pos, accept, f_cols, h->d_mean);
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int check_handle(const b200_edm* h, const char* fn) {
+  if (!h) return fail(B200_ERR_INVALID_ARG, "%s: NULL handle", fn);
+  return B200_OK;
+}
+
+int upload_z(b200_edm* h, const double* z_cols, size_t n, size_t ncols, cudaStream_t st) {
+  if (n != h->Mf) return fail(B200_ERR_INVALID_ARG, "vector length %zu != no_fronts %u", n, h->Mf);
+  for (size_t c = 0; c < ncols; ++c)
+    if (!(z_cols[c * n] == z_cols[c * n]) || z_cols[c * n] == 0.0)
+      return fail(B200_ERR_INVALID_ARG, "column %zu: wave speed z[0] must be finite and non-zero", c);
+  // the pinned staging block is reused: wait for the previous upload to have left it
+  if (h->up_pending) { B200_CUDA(cudaEventSynchronize(h->ev_up)); h->up_pending = false; }
+  B200_TRY(ensure_pinned(h, 2 * n * ncols));
+  memcpy(h->h_pin, z_cols, n * ncols * sizeof(double));
+  B200_CUDA(cudaMemcpyAsync(h->d_z, h->h_pin, n * ncols * sizeof(double), cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaEventRecord(h->ev_up, st));
+  h->up_pending = true;
+  return B200_OK;
+}
+
+template <typename T>
+int compute_batch(b200_edm* h, const double* z_cols, size_t n, size_t ncols, double* f_out) {
+  B200_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t nitems = ncols * h->R;
+  B200_TRY(ensure_batch(h, ncols, nitems));
+  B200_TRY(ensure_ensemble<T>(h, st));
+  B200_TRY(upload_z(h, z_cols, n, ncols, st));
+  B200_TRY(run_prepare<T>(h, ncols, st));
+  B200_TRY(run_evolve<T>(h, 0, nitems, (T*)h->d_pos, h->d_accept, st));
+  B200_TRY(run_reduce<T>(h, ncols, (const T*)h->d_pos, h->d_accept, h->d_f, st));
+  double* h_f = h->h_pin + n * ncols;
+  B200_CUDA(cudaMemcpyAsync(h_f, h->d_f, n * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaMemcpyAsync(&h->last_clamped, h->d_clamped, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (h->debug || h->timing)
+    B200_CUDA(cudaMemcpyAsync(h->last_counters, h->d_counters, sizeof(h->last_counters), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  memcpy(f_out, h_f, n * ncols * sizeof(double));
+  h->last_cols = ncols;
+  if (h->timing) {
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+  }
+  return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b200_edm_model_default(b200_edm_model* m) {
+  if (!m) return;
+  // parameters.hpp:1-15; float literals widened exactly
+  m->vth = (double)1.0f; m->a1 = (double)11.0f; m->a2 = (double)7.0f; m->b1 = (double)5.0f;
+  m->b2 = (double)3.5f; m->I = (double)0.9f; m->L = (double)3.0f; m->tol = 1e-6;
+  m->time_horizon = (double)5.0f; m->counter_max = 100; m->quirks = 0;
+}
+
+int b200_edm_create(const double* params, size_t nparams, uint32_t no_realisations,
+                    uint32_t no_neurons, uint32_t no_fronts, b200_dtype precision, b200_edm** handle) {
+  if (!params || nparams < 1 || !handle) return fail(B200_ERR_INVALID_ARG, "edm_create: NULL / empty argument");
+  if (precision != B200_F64 && precision != B200_F32) return fail(B200_ERR_INVALID_ARG, "edm_create: bad precision");
+  if (no_realisations < 1 || no_neurons < 2 || no_fronts < 1) return fail(B200_ERR_INVALID_ARG, "edm_create: no_realisations >= 1, no_neurons >= 2, no_fronts >= 1 required");
+  if (no_neurons > 16384) return fail(B200_ERR_UNSUPPORTED, "edm_create: no_neurons > 16384 (one CTA holds a whole ring)");
+  *handle = nullptr;
+  B200_TRY(require_device());
+  b200_edm* h = new (std::nothrow) b200_edm();
+  if (!h) return fail(B200_ERR_INVALID_ARG, "out of host memory");
+  h->params.assign(params, params + nparams);
+  b200_edm_model_default(&h->model);
+  h->R = no_realisations; h->N = no_neurons; h->Mf = no_fronts; h->prec = precision;
+  cudaGetDevice(&h->device);
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming);
+  if (e != cudaSuccess) { delete h; return cuda_fail(e, "edm_create", __FILE__, __LINE__); }
+  *handle = h;
+  return B200_OK;
+}
+
+int b200_edm_destroy(b200_edm* h) {
+  if (!h) return B200_OK;
+  cudaSetDevice(h->device);
+  free_ensemble(h);
+  free_batch(h);
+  cudaFree(h->d_clamped); cudaFree(h->d_counters);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_up) cudaEventDestroy(h->ev_up);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return B200_OK;
+}
+
+int b200_edm_set_model(b200_edm* h, const b200_edm_model* m) {
+  B200_TRY(check_handle(h, "edm_set_model"));
+  if (!m) return fail(B200_ERR_INVALID_ARG, "edm_set_model: NULL model");
+  if (!(m->time_horizon > 0) || !(m->L > 0)) return fail(B200_ERR_INVALID_ARG, "edm_set_model: time_horizon and L must be > 0");
+  h->model = *m;
+  h->w_dirty = true;
+  return B200_OK;
+}
+int b200_edm_get_model(const b200_edm* h, b200_edm_model* m) {
+  B200_TRY(check_handle(h, "edm_get_model"));
+  if (!m) return fail(B200_ERR_INVALID_ARG, "edm_get_model: NULL model");
+  *m = h->model;
+  return B200_OK;
+}
+int b200_edm_set_time_horizon(b200_edm* h, double T) {
+  B200_TRY(check_handle(h, "edm_set_time_horizon"));
+  if (!(T > 0)) return fail(B200_ERR_INVALID_ARG, "time horizon must be > 0 (EventDrivenMap.cu:244)");
+  h->model.time_horizon = T;
+  return B200_OK;
+}
+int b200_edm_set_no_realisations(b200_edm* h, uint32_t R) {
+  B200_TRY(check_handle(h, "edm_set_no_realisations"));
+  if (R < 1) return fail(B200_ERR_INVALID_ARG, "no_realisations must be > 0 (EventDrivenMap.cu:251)");
+  if (R != h->R) { h->R = R; h->beta_dirty = true; cudaSetDevice(h->device); free_batch(h); }
+  return B200_OK;
+}
+int b200_edm_set_no_neurons(b200_edm* h, uint32_t N) {
+  B200_TRY(check_handle(h, "edm_set_no_neurons"));
+  if (N < 2) return fail(B200_ERR_INVALID_ARG, "no_neurons must be >= 2 (EventDrivenMap.cu:284)");
+  if (N > 16384) return fail(B200_ERR_UNSUPPORTED, "no_neurons > 16384 (one CTA holds a whole ring)");
+  if (N != h->N) { h->N = N; h->w_dirty = h->beta_dirty = true; cudaSetDevice(h->device); free_batch(h); }
+  return B200_OK;
+}
+int b200_edm_set_param_stddev(b200_edm* h, double sigma) {
+  B200_TRY(check_handle(h, "edm_set_param_stddev"));
+  if (!(sigma >= 0)) return fail(B200_ERR_INVALID_ARG, "sigma must be >= 0 (EventDrivenMap.cu:319)");
+  if (sigma != h->sigma) { h->sigma = sigma; h->beta_dirty = true; }
+  return B200_OK;
+}
+int b200_edm_set_parameter(b200_edm* h, uint32_t par_id, double value) {
+  B200_TRY(check_handle(h, "edm_set_parameter"));
+  if (par_id >= h->params.size()) return fail(B200_ERR_INVALID_ARG, "parameter id %u out of range (EventDrivenMap.cu:326)", par_id);
+  h->params[par_id] = value;
+  if (par_id == 0) h->beta_dirty = true;
+  return B200_OK;
+}
+int b200_edm_set_seed(b200_edm* h, uint64_t seed) {
+  B200_TRY(check_handle(h, "edm_set_seed"));
+  if (seed != h->seed) { h->seed = seed; h->beta_dirty = true; }
+  return B200_OK;
+}
+int b200_edm_get_seed(const b200_edm* h, uint64_t* seed) {
+  B200_TRY(check_handle(h, "edm_get_seed"));
+  if (!seed) return fail(B200_ERR_INVALID_ARG, "edm_get_seed: NULL");
+  *seed = h->seed;
+  return B200_OK;
+}
+int b200_edm_new_seed(b200_edm* h) {
+  B200_TRY(check_handle(h, "edm_new_seed"));
+  // deterministic successor (the reference draws clock(), EventDrivenMap.cu:339)
+  uint64_t x = h->seed + 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  h->seed = x ^ (x >> 31);
+  h->beta_dirty = true;
+  return B200_OK;
+}
+int b200_edm_set_tuning(b200_edm* h, int neurons_per_thread) {
+  B200_TRY(check_handle(h, "edm_set_tuning"));
+  if (neurons_per_thread != 0 && neurons_per_thread != 1 && neurons_per_thread != 2 &&
+      neurons_per_thread != 4 && neurons_per_thread != 8 && neurons_per_thread != 16)
+    return fail(B200_ERR_INVALID_ARG, "neurons per thread must be 0 (auto), 1, 2, 4, 8 or 16");
+  h->npt = neurons_per_thread;
+  return B200_OK;
+}
+
+int b200_edm_compute_f_batch(b200_edm* h, const double* z_cols, size_t n, size_t ncols, double* f_cols_out) {
+  B200_TRY(check_handle(h, "edm_compute_f_batch"));
+  if (!z_cols || !f_cols_out || ncols < 1) return fail(B200_ERR_INVALID_ARG, "edm_compute_f_batch: NULL / empty argument");
+  return h->prec == B200_F64 ? compute_batch<double>(h, z_cols, n, ncols, f_cols_out)
+                             : compute_batch<float>(h, z_cols, n, ncols, f_cols_out);
+}
+
+int b200_edm_compute_f(b200_edm* h, const double* z, size_t n, double* f_out) {
+  return b200_edm_compute_f_batch(h, z, n, 1, f_out);
+}
+
+int b200_edm_compute_dfdu(b200_edm* h, const double* u, size_t n, double eps, double* jac_out, double* f0_out) {
+  B200_TRY(check_handle(h, "edm_compute_dfdu"));
+  if (!u || !jac_out) return fail(B200_ERR_INVALID_ARG, "edm_compute_dfdu: NULL argument");
+  if (n != h->Mf) return fail(B200_ERR_INVALID_ARG, "vector length %zu != no_fronts %u", n, h->Mf);
+  if (!(eps != 0.0)) return fail(B200_ERR_INVALID_ARG, "finite-difference epsilon must be non-zero");
+  // columns 0..n-1: u + eps e_i (NewtonSolver.cpp:184-188), column n: u
+  std::vector<double> zc((n + 1) * n), fc((n + 1) * n);
+  for (size_t c = 0; c <= n; ++c) {
+    for (size_t r = 0; r < n; ++r) zc[c * n + r] = u[r];
+    if (c < n) zc[c * n + c] += eps;
+  }
+  B200_TRY(b200_edm_compute_f_batch(h, zc.data(), n, n + 1, fc.data()));
+  const double inv = pow(eps, -1);  // NewtonSolver.cpp:194
+  for (size_t c = 0; c < n; ++c)
+    for (size_t r = 0; r < n; ++r) jac_out[c * n + r] = (fc[c * n + r] - fc[n * n + r]) * inv;
+  if (f0_out) memcpy(f0_out, &fc[n * n], n * sizeof(double));
+  return B200_OK;
+}
+
+int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_t ncols,
+                              size_t item_begin, size_t item_end, double* pos_dev,
+                              int32_t* accept_dev, void* stream) {
+  B200_TRY(check_handle(h, "edm_evolve_items_dev"));
+  if (!z_cols || ncols < 1 || item_end < item_begin || item_end > ncols * h->R)
+    return fail(B200_ERR_INVALID_ARG, "edm_evolve_items_dev: bad item range / NULL argument");
+  const size_t nitems = item_end - item_begin;
+  if (nitems && (!pos_dev || !accept_dev)) return fail(B200_ERR_INVALID_ARG, "edm_evolve_items_dev: NULL output");
+  B200_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_TRY(ensure_batch(h, ncols, nitems ? nitems : 1));
+  if (h->prec == B200_F64) {
+    B200_TRY(ensure_ensemble<double>(h, st));
+    B200_TRY(upload_z(h, z_cols, n, ncols, st));
+    B200_TRY(run_prepare<double>(h, ncols, st));
+    B200_TRY(run_evolve<double>(h, item_begin, item_end, pos_dev, accept_dev, st));
+  } else {
+    B200_TRY(ensure_ensemble<float>(h, st));
+    B200_TRY(upload_z(h, z_cols, n, ncols, st));
+    B200_TRY(run_prepare<float>(h, ncols, st));
+    B200_TRY(run_evolve<float>(h, item_begin, item_end, (float*)h->d_pos, accept_dev, st));
+    if (nitems)
+      convert_kernel<float, double><<<(unsigned)((nitems * h->Mf + 255) / 256), 256, 0, st>>>((const float*)h->d_pos, pos_dev, nitems * h->Mf);
+    B200_CUDA(cudaGetLastError());
+  }
+  h->last_cols = ncols;
+  return B200_OK;
+}
+
+int b200_edm_reduce_items_dev(b200_edm* h, const double* z_cols, size_t n, size_t ncols,
+                              const double* pos_all_dev, const int32_t* accept_all_dev,
+                              double* f_cols_dev, void* stream) {
+  B200_TRY(check_handle(h, "edm_reduce_items_dev"));
+  if (!z_cols || !pos_all_dev || !accept_all_dev || !f_cols_dev || ncols < 1)
+    return fail(B200_ERR_INVALID_ARG, "edm_reduce_items_dev: NULL / empty argument");
+  B200_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_TRY(ensure_batch(h, ncols, 1));
+  B200_TRY(upload_z(h, z_cols, n, ncols, st));
+  if (h->prec == B200_F64) {
+    B200_TRY(run_reduce<double>(h, ncols, pos_all_dev, accept_all_dev, f_cols_dev, st));
+  } else {
+    // positions were widened to double for the exchange; narrow them back so the mean is
+    // accumulated in float exactly as the single-GPU path does
+    const size_t nitems = ncols * h->R;
+    B200_TRY(ensure_batch(h, ncols, nitems));
+    convert_kernel<double, float><<<(unsigned)((nitems * h->Mf + 255) / 256), 256, 0, st>>>(pos_all_dev, (float*)h->d_pos, nitems * h->Mf);
+    B200_TRY(run_reduce<float>(h, ncols, (const float*)h->d_pos, accept_all_dev, f_cols_dev, st));
+  }
+  return B200_OK;
+}
+
+int b200_edm_set_debug(b200_edm* h, int on) {
+  B200_TRY(check_handle(h, "edm_set_debug"));
+  h->debug = on ? 1 : 0;
+  return B200_OK;
+}
+
+int b200_edm_enable_timing(b200_edm* h, int on) {
+  B200_TRY(check_handle(h, "edm_enable_timing"));
+  h->timing = on ? 1 : 0;
+  return B200_OK;
+}
+
+int b200_edm_last_evolve_ms(const b200_edm* h, double* ms) {
+  B200_TRY(check_handle(h, "edm_last_evolve_ms"));
+  if (!ms) return fail(B200_ERR_INVALID_ARG, "NULL");
+  *ms = h->last_ms;
+  return B200_OK;
+}
+
+int b200_edm_last_event_total(const b200_edm* h, uint64_t* events) {
+  B200_TRY(check_handle(h, "edm_last_event_total"));
+  if (!events) return fail(B200_ERR_INVALID_ARG, "NULL");
+  *events = h->last_counters[0];
+  return B200_OK;
+}
+
+int b200_edm_last_counters(const b200_edm* h, uint64_t out[4]) {
+  B200_TRY(check_handle(h, "edm_last_counters"));
+  if (!out) return fail(B200_ERR_INVALID_ARG, "NULL");
+  for (int i = 0; i < 4; ++i) out[i] = h->last_counters[i];
+  return B200_OK;
+}
+
+int b200_edm_last_init_clamped(const b200_edm* h, int* clamped) {
+  B200_TRY(check_handle(h, "edm_last_init_clamped"));
+  if (!clamped) return fail(B200_ERR_INVALID_ARG, "NULL");
+  *clamped = h->last_clamped;
+  return B200_OK;
+}
+
+int b200_edm_debug_fetch(b200_edm* h, b200_edm_debug_what what, void* out, size_t bytes) {
+  B200_TRY(check_handle(h, "edm_debug_fetch"));
+  if (!out) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: NULL output");
+  if (!h->debug) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: debug flag is off (SetDebugFlag)");
+  if (h->last_cols == 0) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: no evaluation has run yet");
+  B200_CUDA(cudaSetDevice(h->device));
+  const size_t C = h->last_cols, R = h->R, N = h->N, Mf = h->Mf, es = esize(h);
+  const void* src = nullptr;
+  size_t count = 0;
+  bool real = false, is_int = false;
+  switch (what) {
+    case B200_EDM_DBG_INIT_INDEX: src = h->d_init; count = C * Mf; is_int = true; break;
+    case B200_EDM_DBG_LIFT_V: src = h->d_lv; count = C * N; real = true; break;
+    case B200_EDM_DBG_LIFT_S: src = h->d_ls; count = C * N; real = true; break;
+    case B200_EDM_DBG_LAST_INDEX: src = h->d_last_i; count = C * R * Mf; is_int = true; break;
+    case B200_EDM_DBG_LAST_TIME: src = h->d_last_t; count = C * R * Mf; real = true; break;
+    case B200_EDM_DBG_CROSSED_INDEX: src = h->d_cross_i; count = C * R * Mf; is_int = true; break;
+    case B200_EDM_DBG_CROSSED_TIME: src = h->d_cross_t; count = C * R * Mf; real = true; break;
+    case B200_EDM_DBG_ACCEPT: src = h->d_accept; count = C * R; is_int = true; break;
+    case B200_EDM_DBG_POSITION: src = h->d_pos; count = C * R * Mf; real = true; break;
+    case B200_EDM_DBG_EVENT_COUNT: src = h->d_evcount; count = C * R; is_int = true; break;
+    case B200_EDM_DBG_MEAN: src = h->d_mean; count = C * Mf; break;  // always double
+    case B200_EDM_DBG_BETA: src = h->beta; count = R * N; real = true; break;
+    case B200_EDM_DBG_COUPLING: src = h->w; count = N; real = true; break;
+    default: return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: unknown array id %d", (int)what);
+  }
+  const size_t out_es = is_int ? 4 : 8;
+  if (bytes < count * out_es) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: buffer of %zu B, %zu B needed", bytes, count * out_es);
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  if (what == B200_EDM_DBG_BETA && !src) {  // homogeneous ensemble: beta is the mean everywhere
+    double* o = (double*)out;
+    const double b = h->prec == B200_F64 ? h->params[0] : (double)(float)h->params[0];
+    for (size_t i = 0; i < count; ++i) o[i] = b;
+    return B200_OK;
+  }
+  if (!src) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: array not available");
+  if (real && es == 4) {
+    std::vector<float> tmp(count);
+    B200_CUDA(cudaMemcpy(tmp.data(), src, count * 4, cudaMemcpyDeviceToHost));
+    double* o = (double*)out;
+    for (size_t i = 0; i < count; ++i) o[i] = (double)tmp[i];
+  } else {
+    B200_CUDA(cudaMemcpy(out, src, count * out_es, cudaMemcpyDeviceToHost));
+  }
+  return B200_OK;
+}
+
+}  // extern "C"
