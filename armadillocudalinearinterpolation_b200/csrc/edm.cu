@@ -59,7 +59,7 @@ struct Consts {
   unsigned counter_max;
 };
 
-// counter-based standard normal (same construction as oracle_normal)
+// counter-based standard normal (the CPU restatement mirrors this construction)
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -170,7 +170,9 @@ edm_prepare_kernel(Consts<T> k, unsigned N, unsigned Mf, T beta, const double* _
   const T s_d1 = beta * a1 * (c / (cb1 - beta)), s_d2 = beta * a2 * (c / (cb2 - beta));
 
   for (unsigned j = threadIdx.x; j < N; j += blockDim.x) {
-    const T x = L - (T)(2 * L / N) * j;
+    // two rounded operations (no FMA): a grid point that coincides with a front must land on
+    // the same side of it as in the CPU restatement
+    const T x = sub_rn(L, mul_rn((T)(2 * L / N), (T)j));
     // factors that depend on x only
     const T ex_beta = M<T>::exp_((x / c) * (one - beta));
     const T ex_m1 = M<T>::exp_(x * ((one - cb1) / c)), ex_m2 = M<T>::exp_(x * ((one - cb2) / c));
@@ -635,8 +637,10 @@ struct b200_edm {
   int debug = 0, timing = 0, npt = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_up = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_up = nullptr, ev_done = nullptr;
   bool up_pending = false;
+  cudaStream_t last_stream = nullptr;
+  bool done_pending = false;
   // ensemble-level device state
   void* w = nullptr;
   void* beta = nullptr;
@@ -850,6 +854,19 @@ int run_reduce(b200_edm* h, size_t ncols, const T* pos, const int32_t* accept, d
   return B200_OK;
 }
 
+// The handle's buffers are shared by every call: work issued on a different stream than the
+// previous call first waits for that call's tail.
+int order_after_previous(b200_edm* h, cudaStream_t st) {
+  if (h->done_pending && st != h->last_stream) B200_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+  return B200_OK;
+}
+int mark_done(b200_edm* h, cudaStream_t st) {
+  B200_CUDA(cudaEventRecord(h->ev_done, st));
+  h->last_stream = st;
+  h->done_pending = true;
+  return B200_OK;
+}
+
 int check_handle(const b200_edm* h, const char* fn) {
   if (!h) return fail(B200_ERR_INVALID_ARG, "%s: NULL handle", fn);
   return B200_OK;
@@ -875,6 +892,7 @@ int compute_batch(b200_edm* h, const double* z_cols, size_t n, size_t ncols, dou
   B200_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const size_t nitems = ncols * h->R;
+  B200_TRY(order_after_previous(h, st));
   B200_TRY(ensure_batch(h, ncols, nitems));
   B200_TRY(ensure_ensemble<T>(h, st));
   B200_TRY(upload_z(h, z_cols, n, ncols, st));
@@ -887,6 +905,7 @@ int compute_batch(b200_edm* h, const double* z_cols, size_t n, size_t ncols, dou
   if (h->debug || h->timing)
     B200_CUDA(cudaMemcpyAsync(h->last_counters, h->d_counters, sizeof(h->last_counters), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
+  h->done_pending = false;
   memcpy(f_out, h_f, n * ncols * sizeof(double));
   h->last_cols = ncols;
   if (h->timing) {
@@ -927,6 +946,7 @@ int b200_edm_create(const double* params, size_t nparams, uint32_t no_realisatio
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "edm_create", __FILE__, __LINE__); }
   *handle = h;
   return B200_OK;
@@ -942,6 +962,7 @@ int b200_edm_destroy(b200_edm* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_up) cudaEventDestroy(h->ev_up);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return B200_OK;
@@ -1063,6 +1084,7 @@ int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
   if (nitems && (!pos_dev || !accept_dev)) return fail(B200_ERR_INVALID_ARG, "edm_evolve_items_dev: NULL output");
   B200_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  B200_TRY(order_after_previous(h, st));
   B200_TRY(ensure_batch(h, ncols, nitems ? nitems : 1));
   if (h->prec == B200_F64) {
     B200_TRY(ensure_ensemble<double>(h, st));
@@ -1079,7 +1101,7 @@ int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     B200_CUDA(cudaGetLastError());
   }
   h->last_cols = ncols;
-  return B200_OK;
+  return mark_done(h, st);
 }
 
 int b200_edm_reduce_items_dev(b200_edm* h, const double* z_cols, size_t n, size_t ncols,
@@ -1090,6 +1112,7 @@ int b200_edm_reduce_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     return fail(B200_ERR_INVALID_ARG, "edm_reduce_items_dev: NULL / empty argument");
   B200_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  B200_TRY(order_after_previous(h, st));
   B200_TRY(ensure_batch(h, ncols, 1));
   B200_TRY(upload_z(h, z_cols, n, ncols, st));
   if (h->prec == B200_F64) {
@@ -1102,7 +1125,7 @@ int b200_edm_reduce_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     convert_kernel<double, float><<<(unsigned)((nitems * h->Mf + 255) / 256), 256, 0, st>>>(pos_all_dev, (float*)h->d_pos, nitems * h->Mf);
     B200_TRY(run_reduce<float>(h, ncols, (const float*)h->d_pos, accept_all_dev, f_cols_dev, st));
   }
-  return B200_OK;
+  return mark_done(h, st);
 }
 
 int b200_edm_set_debug(b200_edm* h, int on) {

@@ -1,0 +1,109 @@
+"""Finite-difference Jacobian sharded over GPUs — one process per GPU, torch.distributed.
+
+The reference forms the Jacobian with n sequential ComputeF calls (NewtonSolver.cpp:181-195,
+Stability.cpp:95-109).  Here the n+1 evaluations are one batch of (column, realisation) work
+items; rank g evolves a contiguous slice of the items on its GPU (b200_edm_evolve_items_dev),
+the restricted front positions + accept flags are exchanged with ONE all-gather (NCCL over
+NVLink; a few hundred kB), and every rank forms the masked means in the same fixed order
+(b200_edm_reduce_items_dev) — so the Jacobian is bitwise independent of the number of GPUs.
+Sharding by items rather than by columns keeps all 8 GPUs busy even for n = 3.
+"""
+import numpy as np
+
+
+def partition_items(n_items, world):
+    """Contiguous, equally padded slices: returns (per_rank, [(lo, hi)] * world)."""
+    per = (n_items + world - 1) // world
+    return per, [(min(r * per, n_items), min((r + 1) * per, n_items)) for r in range(world)]
+
+
+def fd_columns(u, eps):
+    """Evaluation points of the forward-difference Jacobian: columns 0..n-1 are u + eps e_i
+    (NewtonSolver.cpp:184-188), column n is u itself."""
+    u = np.asarray(u, np.float64).ravel()
+    n = u.size
+    z = np.repeat(u[:, None], n + 1, axis=1)
+    z[np.arange(n), np.arange(n)] += eps
+    return np.asfortranarray(z)
+
+
+def fd_jacobian_from_columns(f_cols, eps):
+    """J(:, i) = (F(u + eps e_i) - F(u)) * pow(eps, -1)   (NewtonSolver.cpp:194)."""
+    n = f_cols.shape[0]
+    return np.asfortranarray((f_cols[:, :n] - f_cols[:, n:n + 1]) * eps ** -1), f_cols[:, n].copy()
+
+
+class GpuEngine:
+    """Evolve / reduce on this rank's B200 through the C-ABI."""
+
+    def __init__(self, parameters, noReal, noNeurons=1024, noFronts=3, precision="f64"):
+        import torch
+        from .edm import EventDrivenMap
+        self.torch = torch
+        self.map = EventDrivenMap(parameters, noReal, noNeurons=noNeurons, noFronts=noFronts, precision=precision)
+        self.R, self.M = int(noReal), int(noFronts)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def _stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def evolve(self, z_cols, lo, hi, out):
+        """out: (per, M + 1) float64 device tensor; columns 0..M-1 positions, column M accept."""
+        t = self.torch
+        n = hi - lo
+        pos = t.empty((max(n, 1), self.M), dtype=t.float64, device=self.device)
+        acc = t.empty((max(n, 1),), dtype=t.int32, device=self.device)
+        if n:
+            self.map.EvolveItemsDev(z_cols, lo, hi, pos, acc, stream=self._stream())
+            out[:n, :self.M] = pos[:n]
+            out[:n, self.M] = acc[:n].to(t.float64)
+
+    def reduce(self, z_cols, gathered, n_items):
+        t = self.torch
+        pos = gathered[:n_items, :self.M].contiguous()
+        acc = gathered[:n_items, self.M].to(t.int32).contiguous()
+        ncols = z_cols.shape[1]
+        f = t.empty((ncols, self.M), dtype=t.float64, device=self.device)
+        self.map.ReduceItemsDev(z_cols, pos, acc, f, stream=self._stream())
+        return f.cpu().numpy().T  # (n, ncols)
+
+    def empty(self, rows):
+        return self.torch.zeros((rows, self.M + 1), dtype=self.torch.float64, device=self.device)
+
+
+class ShardedJacobian:
+    """AbstractNonlinearProblem + AbstractNonlinearProblemJacobian over `world` ranks.
+
+    `group` is the torch.distributed module (or None for a single process); `engine` defaults
+    to the GPU engine — the CPU tests inject a host engine to exercise the sharding logic with
+    the gloo backend."""
+
+    def __init__(self, parameters, noReal, noNeurons=1024, noFronts=3, precision="f64", group=None, engine=None):
+        self.dist = group if (group is not None and group.is_initialized()) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.engine = engine or GpuEngine(parameters, noReal, noNeurons, noFronts, precision)
+        self.R, self.M = int(noReal), int(noFronts)
+
+    def ComputeFBatch(self, z_cols):
+        z_cols = np.asfortranarray(z_cols, np.float64)
+        ncols = z_cols.shape[1]
+        n_items = ncols * self.R
+        per, slices = partition_items(n_items, self.world)
+        lo, hi = slices[self.rank]
+        local = self.engine.empty(per)
+        self.engine.evolve(z_cols, lo, hi, local)
+        if self.world > 1:
+            gathered = self.engine.empty(per * self.world)
+            self.dist.all_gather_into_tensor(gathered, local)
+        else:
+            gathered = local
+        return self.engine.reduce(z_cols, gathered, n_items)
+
+    def ComputeF(self, u):
+        return self.ComputeFBatch(np.asarray(u, np.float64).reshape(-1, 1))[:, 0]
+
+    def ComputeDFDU(self, u, eps, return_f0=False):
+        f_cols = self.ComputeFBatch(fd_columns(u, eps))
+        J, f0 = fd_jacobian_from_columns(f_cols, eps)
+        return (J, f0) if return_f0 else J

@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json metric:
+"interp points/s & map evals/s at 1/2/4/8 B200; achieved HBM GB/s vs peak").
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload of the headline line (BASELINE.json configs[1]): 2-D bilinear interpolation of a
+4096x4096 float64 column-major grid at 1e8 scattered queries per GPU ("step" = one pass over
+the 1e8 queries).  `value` is device-resident throughput (CUDA events on the launching stream);
+`e2e` is the same pass through the host-buffer C-ABI call b200_interp2_scattered with pinned
+host buffers, H2D/D2H inside the timed region.  `extra` carries the other BASELINE configs
+(1-D interp at 1e6 knots / 1e7 queries, one map evaluation of the parameters.hpp default
+ensemble, the finite-difference Jacobian) measured the same way, shorter.
+
+N > 1: launched by torchrun, one rank per GPU.  The interpolation shards by queries with no
+collective (weak scaling: 1e8 queries per rank).  The Jacobian in `extra` shards its
+(column, realisation) work items over the ranks and gathers positions with one NCCL all-gather.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX = NY = 4096
+NQ = 100_000_000
+ALG_BYTES_PER_QUERY = 24            # xq, yq in + zq out, float64
+ALG_BYTES_GRID = 8 * NX * NY        # the grid is read once
+Z_DRIVER = np.array([np.float32(0.3310), np.float32(0.6914), np.float32(1.3557)], dtype=np.float64)
+BETA = float(np.float32(13.0589))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_grid():
+    rng = np.random.default_rng(2234)
+    x = np.linspace(0.0, 1.0, NX)
+    y = np.linspace(0.0, 1.0, NY)
+    z = np.sin(2 * np.pi * x)[None, :] * np.cos(2 * np.pi * y)[:, None] + 0.1 * rng.standard_normal((NY, NX))
+    return x, y, np.asfortranarray(z)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_interp2(sample, threads, grid=None):
+    """The reference-side CPU path for configs[1]: the oracle's restatement of arma::interp2
+    applied per scattered point, OpenMP over queries.  Returns points/s."""
+    from oracle import oracle_py as O
+    x, y, z = grid or make_grid()
+    rng = np.random.default_rng(2235)
+    xq = rng.random(sample); yq = rng.random(sample)
+    O.interp2_scattered(x, y, z, xq[:100000], yq[:100000], nthreads=threads)  # touch + warm
+    t = time.perf_counter()
+    O.interp2_scattered(x, y, z, xq, yq, nthreads=threads)
+    return sample / (time.perf_counter() - t)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Armadillo is absent
+    from the image and the reference has no interp2 call site, so this is the
+    oracle port of arma::interp2's algorithm, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = cpu_threads()
+    grid = make_grid()
+    sample = 20_000_000
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_interp2(2_000_000, threads, grid)
+    vals = [cpu_interp2(sample, threads, grid) for _ in range(max(1, min(args.steps, 5)))]
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "interp points/s (2-D bilinear, 4096x4096 f64 grid, scattered queries)",
+            "value": v, "unit": "points/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1,
+            "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "interp2_scattered_f64_4096x4096", "sample": f"{sample} queries per step (of 1e8)"},
+            "cpu_baseline": {"value": v, "unit": "points/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} of 1e8 scattered queries, OpenMP over queries"},
+            "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def time_steps(torch, fn, steps, warmup, dist=None):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events on
+    the current stream; returns total ms (max over ranks)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        dist.barrier()
+    return ms
+
+
+def wall_steps(torch, fn, steps, warmup, dist=None):
+    """Host-visible timing for calls that synchronise internally (host-buffer C-ABI entry points)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0)
+    if dist:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        dist.barrier()
+    return ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import armadillocudalinearinterpolation_b200 as B
+    from armadillocudalinearinterpolation_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    B.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+    n_gpus = world
+
+    # ---------------- headline: interp2 scattered, 1e8 queries / GPU ----------------
+    grid = make_grid()
+    plan = B.Interp2Plan(*grid)
+    g = torch.Generator(device="cuda").manual_seed(2235 + rank)
+    xq = torch.rand(NQ, generator=g, device="cuda", dtype=torch.float64)
+    yq = torch.rand(NQ, generator=g, device="cuda", dtype=torch.float64)
+    zq = torch.empty_like(xq)
+    step = lambda: plan.scattered(xq, yq, out=zq)
+    sampler = ClockSampler(local)
+    time_steps(torch, step, 1, args.warmup, dist)       # warm-up outside the sampled window
+    sampler.start()
+    ms = time_steps(torch, step, args.steps, 0, dist)
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    value = n_gpus * NQ / (ms_per_step * 1e-3)
+    peak, peak_src = measured_peak()
+    alg_bytes = ALG_BYTES_PER_QUERY * NQ + ALG_BYTES_GRID
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("interp2_scattered_f64", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---------------- e2e: host buffers through the C-ABI ----------------
+    hx = torch.empty(NQ, dtype=torch.float64).pin_memory()
+    hy = torch.empty(NQ, dtype=torch.float64).pin_memory()
+    hz = torch.empty(NQ, dtype=torch.float64).pin_memory()
+    hx.copy_(xq); hy.copy_(yq)
+    torch.cuda.synchronize()
+    hxn, hyn, hzn = hx.numpy(), hy.numpy(), hz.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms = wall_steps(torch, lambda: plan.scattered(hxn, hyn, out=hzn), e2e_steps, 1, dist) / e2e_steps
+    e2e_val = n_gpus * NQ / (e2e_ms * 1e-3)
+    check = float(np.abs(hzn[:1000] - zq[:1000].cpu().numpy()).max())
+    del hx, hy, hz
+
+    line = {"metric": "interp points/s (2-D bilinear, 4096x4096 f64 grid, 1e8 scattered queries)",
+            "value": value, "unit": "points/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "interp2_scattered_f64_4096x4096_1e8_queries_per_gpu",
+                       "grid": "4096x4096 float64 column-major (128 MiB), seed 2234",
+                       "queries": "1e8 (x,y) ~ U[0,1]^2 per GPU, unsorted, seed 2235+rank",
+                       "l2": "inputs larger than L2 (1.6 GB of queries + 0.8 GB of outputs per step)",
+                       "parallelism": f"query shards x{n_gpus}, no collective"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "points/s", "h2d_bytes_per_step": 16 * NQ, "d2h_bytes_per_step": 8 * NQ,
+                    "ms_per_step": e2e_ms, "api": "b200_interp2_scattered (pinned host buffers, 2-slot chunked pipeline)",
+                    "max_abs_diff_vs_device_path": check},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "interp2_scattered_vec_kernel<double>",
+                         "algorithmic_bytes_per_launch": alg_bytes}}
+
+    # ---------------- secondary workloads ----------------
+    if not args.no_extra:
+        extra = {}
+        # configs[0]: 1-D, 1e6 knots, 1e7 queries; 8 rotating query/output buffer pairs (1.28 GB)
+        # so that consecutive launches never find their streams in L2
+        rng = np.random.default_rng(1234)
+        ng, ni, nbuf = 1_000_000, 10_000_000, 8
+        for kind in ("uniform", "nonuniform"):
+            xg = np.linspace(0.0, 1.0, ng) if kind == "uniform" else np.cumsum(0.5 + rng.random(ng))
+            xg = (xg - xg[0]) / (xg[-1] - xg[0])
+            yg = np.sin(2 * np.pi * xg) + 0.1 * np.random.default_rng(1235).standard_normal(ng)
+            p1 = B.Interp1Plan(xg, yg)
+            for order in ("unsorted", "sorted"):
+                g1 = torch.Generator(device="cuda").manual_seed(1236)
+                qs = [torch.rand(ni, generator=g1, device="cuda", dtype=torch.float64) for _ in range(nbuf)]
+                if order == "sorted":
+                    qs = [q.sort().values for q in qs]
+                outs = [torch.empty_like(q) for q in qs]
+                state = {"i": 0}
+
+                def step1():
+                    i = state["i"] % nbuf
+                    state["i"] += 1
+                    p1(qs[i], out=outs[i])
+                k1 = max(args.steps, 16)
+                ms1 = time_steps(torch, step1, k1, 3, dist) / k1
+                gbs = (16 * ni + 16 * ng) / (ms1 * 1e-3) / 1e9
+                extra[f"interp1_f64_1e6knots_1e7queries_{kind}_{order}"] = {
+                    "points_per_s": n_gpus * ni / (ms1 * 1e-3), "ms_per_launch": ms1, "lookup_mode": p1.lookup_mode,
+                    "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+                del qs, outs
+            p1.close()
+        # configs[1] grid shape (Armadillo's own interp2 API): 1e4 x 1e4 sorted points
+        g2 = torch.Generator(device="cuda").manual_seed(2236)
+        xi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
+        yi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
+        msg = time_steps(torch, lambda: plan.grid(xi, yi), max(5, args.steps // 2), 3, dist) / max(5, args.steps // 2)
+        gb = (8 * 1e8 + ALG_BYTES_GRID + 16 * 1e4) / (msg * 1e-3) / 1e9
+        extra["interp2_grid_f64_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msg * 1e-3), "ms_per_launch": msg,
+                                             "algorithmic_GBps": gb, "roofline_frac": gb / peak}
+        # configs[2]: one map evaluation, parameters.hpp default ensemble (R=1000, N=1024, M=3, T=5)
+        for sigma in (0.0, 0.5):
+            m = B.EventDrivenMap([BETA], 1000, noNeurons=1024)
+            m.SetParameterStdDev(sigma); m.SetSeed(42); m.EnableTiming(True)
+            for _ in range(3):
+                m.ComputeF(Z_DRIVER)
+            reps = 10
+            t0 = time.perf_counter()
+            evolve_ms = []
+            for _ in range(reps):
+                m.ComputeF(Z_DRIVER)
+                evolve_ms.append(m.LastEvolveMs())
+            call_ms = 1e3 * (time.perf_counter() - t0) / reps
+            cnt = m.LastCounters()
+            extra[f"map_eval_R1000_N1024_sigma{sigma}"] = {
+                "evals_per_s_per_gpu": 1e3 / call_ms, "ms_per_compute_f": call_ms, "evolve_kernel_ms": float(np.mean(evolve_ms)),
+                "events": cnt["events"], "neuron_event_updates_per_s": cnt["events"] * 1024 / (np.mean(evolve_ms) * 1e-3),
+                "candidates": cnt["candidates"], "newton_its": cnt["newton_its"]}
+            m.close()
+        # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
+        # items sharded over the ranks, positions gathered with one NCCL all-gather
+        jm = parallel.ShardedJacobian([BETA], 1000, noNeurons=1024, group=dist)
+        for _ in range(3):
+            jm.ComputeDFDU(Z_DRIVER, 1e-2)
+        reps = 10
+        msj = wall_steps(torch, lambda: jm.ComputeDFDU(Z_DRIVER, 1e-2), reps, 0, dist) / reps
+        extra["fd_jacobian_n3_R1000_N1024"] = {"jacobians_per_s": 1e3 / msj, "map_evals_per_s": 4e3 / msj,
+                                               "ms_per_jacobian": msj, "ranks": n_gpus, "scaling": "strong",
+                                               "collective": "all_gather of (items x 3) positions" if world > 1 else "none"}
+        line["extra"] = extra
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+        th = cpu_threads()
+        sample = 20_000_000
+        v = cpu_interp2(sample, th, grid)
+        line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": th, "kind": "port",
+                                "sample": f"{sample} of 1e8 scattered queries, oracle restatement of arma::interp2, OpenMP over queries"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,7 @@ def interp2_scattered(x, y, z, xq, yq, extrap=np.nan, nthreads=1):
 
 def edm_cfg(**kw):
     c = EdmCfg()
+    lib().oracle_edm_cfg_default.argtypes = [C.c_void_p]
     lib().oracle_edm_cfg_default(C.byref(c))
     keep = {}
     for k, v in kw.items():
@@ -170,7 +171,10 @@ def edm_compute_dfdu(cfg, u, eps, nthreads=1):
 
 def edm_beta(cfg):
     out = np.empty((cfg.R, cfg.N))
-    lib().oracle_edm_beta(C.addressof(cfg), _p(out))
+    fn = lib().oracle_edm_beta
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p]
+    fn(C.addressof(cfg), _p(out))
     return out
 
 

