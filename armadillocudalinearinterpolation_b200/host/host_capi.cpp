@@ -1,0 +1,152 @@
+// host_capi.cpp — a few C entry points over the C++ host layer so that the test-suite (pytest,
+// ctypes) can drive NewtonSolver / Stability / EventDrivenMapB200 exactly as a C++ user would.
+#include <cmath>
+#include <cstring>
+#include <sstream>
+#include "EventDrivenMapB200.hpp"
+#include "NewtonSolver.hpp"
+#include "Stability.hpp"
+
+namespace {
+thread_local std::string g_err;
+
+// Analytic test problems (no GPU): F_i(u) = u_i^2 - (i+2) + 0.1 * u_{(i+1) mod n}
+class QuadraticProblem : public AbstractNonlinearProblem, public AbstractNonlinearProblemJacobian {
+ public:
+  int calls = 0, post = 0;
+  void ComputeF(const arma::vec& u, arma::vec& f) {
+    const arma::uword n = u.n_elem;
+    f.set_size(n);
+    for (arma::uword i = 0; i < n; ++i) f(i) = u(i) * u(i) - double(i + 2) + 0.1 * u((i + 1) % n);
+    ++calls;
+  }
+  void PostProcess() { ++post; }
+  void ComputeDFDU(const arma::vec& u, arma::mat& J) {
+    const arma::uword n = u.n_elem;
+    J.zeros(n, n);
+    for (arma::uword i = 0; i < n; ++i) { J(i, i) += 2.0 * u(i); J(i, (i + 1) % n) += 0.1; }
+  }
+};
+
+// Linear map problem F(u) = A u - u with user matrix A (for the Stability tests)
+class LinearProblem : public AbstractNonlinearProblem {
+ public:
+  arma::mat A;
+  void ComputeF(const arma::vec& u, arma::vec& f) { f = A * u - u; }
+};
+}  // namespace
+
+extern "C" {
+
+const char* b200_host_last_error() { return g_err.c_str(); }
+
+// Newton on the analytic problem.  use_jacobian: 0 = solver's finite differences, 1 = analytic.
+// out: solution[n], history[max_it+1] (NaN padded), returns iterations*4 + converged*2 + post_called
+int b200_host_newton_quadratic(int n, const double* guess, double tol, int max_it, double eps, double damping,
+                               int use_jacobian, double* solution, double* history, int* n_history,
+                               int* f_calls, double* jac_out) {
+  try {
+    QuadraticProblem prob;
+    arma::vec g(n), sol(n), hist;
+    for (int i = 0; i < n; ++i) g(i) = guess[i];
+    NewtonSolver::ParameterList pars;
+    pars.printOutput = false;
+    NewtonSolver* solver = use_jacobian ? new NewtonSolver(&prob, &prob, &g, &pars) : new NewtonSolver(&prob, &g, &pars);
+    // edits after construction must apply (Driver.cu:37)
+    pars.tolerance = tol; pars.maxIterations = max_it; pars.finiteDifferenceEpsilon = eps; pars.damping = damping;
+    AbstractNonlinearSolver::ExitFlagType flag;
+    arma::mat J(n, n);
+    solver->Solve(sol, hist, flag, jac_out ? &J : NULL);
+    delete solver;
+    for (int i = 0; i < n; ++i) solution[i] = sol(i);
+    *n_history = (int)hist.n_elem;
+    for (arma::uword i = 0; i < hist.n_elem; ++i) history[i] = hist(i);
+    *f_calls = prob.calls;
+    if (jac_out) std::memcpy(jac_out, J.memptr(), sizeof(double) * n * n);
+    return ((int)hist.n_elem - 1) * 4 + (flag == AbstractNonlinearSolver::ExitFlagType::converged ? 2 : 0) + (prob.post == 1 ? 1 : 0);
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// Stability of the linear map u -> A u given as F(u) = A u - u.  type: 0 flow, 1 map, 2 equationFree.
+int b200_host_stability_linear(int n, const double* A_colmajor, int type, double eps, int via_matrix,
+                               double* eig_re, double* eig_im) {
+  try {
+    LinearProblem prob;
+    prob.A.set_size(n, n);
+    std::memcpy(prob.A.memptr(), A_colmajor, sizeof(double) * n * n);
+    Stability::ProblemType t = type == 0 ? Stability::ProblemType::flow : type == 1 ? Stability::ProblemType::map : Stability::ProblemType::equationFree;
+    Stability st(t, &prob);
+    st.SetFiniteDifferenceEpsilon(eps);
+    arma::vec u(n);
+    for (int i = 0; i < n; ++i) u(i) = 0.1 * (i + 1);
+    if (eig_re) {
+      arma::cx_vec w = via_matrix ? arma::eig_gen(prob.A) : st.ComputeEigenvalues(u);
+      for (int i = 0; i < n; ++i) { eig_re[i] = w(i).real(); eig_im[i] = w(i).imag(); }
+    }
+    return via_matrix ? st.ComputeNumUnstableEigenvalues(prob.A) : st.ComputeNumUnstableEigenvalues(u);
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+int b200_host_solve(int n, const double* A_colmajor, const double* b, double* x) {
+  try {
+    arma::mat A(n, n);
+    std::memcpy(A.memptr(), A_colmajor, sizeof(double) * n * n);
+    arma::vec bb(n), xx;
+    for (int i = 0; i < n; ++i) bb(i) = b[i];
+    if (!arma::solve(xx, A, bb)) return 1;
+    for (int i = 0; i < n; ++i) x[i] = xx(i);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// ---- GPU: the drop-in class driven by the host solvers (needs a B200) ----
+// mode 0: NewtonSolver 3-arg ctor (its own sequential FD loop over ComputeF)
+// mode 1: NewtonSolver 4-arg ctor (EventDrivenMapB200::ComputeDFDU, one batched launch)
+int b200_host_edm_newton(double beta, unsigned R, unsigned N, const double* guess, int n, double tol, int max_it,
+                         double eps, int mode, double sigma, double* solution, double* history, int* n_history,
+                         double* jac_out) {
+  try {
+    arma::vec p(1);
+    p(0) = beta;
+    EventDrivenMapB200 map(&p, R, N, (unsigned)n);
+    map.SetPrintOutput(false);
+    map.SetFiniteDifferenceEpsilon(eps);
+    if (sigma > 0) map.SetParameterStdDev((float)sigma);
+    arma::vec g(n), sol(n), hist;
+    for (int i = 0; i < n; ++i) g(i) = guess[i];
+    NewtonSolver::ParameterList pars;
+    pars.tolerance = tol; pars.maxIterations = max_it; pars.printOutput = false; pars.finiteDifferenceEpsilon = eps;
+    NewtonSolver* solver = mode ? new NewtonSolver(&map, &map, &g, &pars) : new NewtonSolver(&map, &g, &pars);
+    AbstractNonlinearSolver::ExitFlagType flag;
+    arma::mat J(n, n);
+    solver->Solve(sol, hist, flag, &J);
+    delete solver;
+    for (int i = 0; i < n; ++i) solution[i] = sol(i);
+    *n_history = (int)hist.n_elem;
+    for (arma::uword i = 0; i < hist.n_elem; ++i) history[i] = hist(i);
+    if (jac_out) std::memcpy(jac_out, J.memptr(), sizeof(double) * n * n);
+    return flag == AbstractNonlinearSolver::ExitFlagType::converged ? 1 : 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// Stability (equationFree) of the map at u: number of unstable eigenvalues + the spectrum of I + J
+int b200_host_edm_stability(double beta, unsigned R, unsigned N, const double* u_in, int n, double eps, int mode,
+                            double* eig_re, double* eig_im) {
+  try {
+    arma::vec p(1);
+    p(0) = beta;
+    EventDrivenMapB200 map(&p, R, N, (unsigned)n);
+    map.SetPrintOutput(false);
+    map.SetFiniteDifferenceEpsilon(eps);
+    arma::vec u(n);
+    for (int i = 0; i < n; ++i) u(i) = u_in[i];
+    Stability st = mode ? Stability(Stability::ProblemType::equationFree, &map, &map)
+                        : Stability(Stability::ProblemType::equationFree, &map);
+    st.SetFiniteDifferenceEpsilon(eps);
+    arma::cx_vec w = st.ComputeEigenvalues(u);
+    for (int i = 0; i < n; ++i) { eig_re[i] = w(i).real(); eig_im[i] = w(i).imag(); }
+    return st.ComputeNumUnstableEigenvalues(u);
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+}  // extern "C"

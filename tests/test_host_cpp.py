@@ -1,0 +1,151 @@
+"""The C++ host layer (armadillocudalinearinterpolation_b200/host): the reference's solver
+interfaces re-implemented over the Armadillo shim, and the drop-in map class.  CPU tests drive
+NewtonSolver / Stability on analytic problems through host_capi.cpp; GPU tests drive the real
+EventDrivenMapB200 through the same solvers and compare with the oracle's Newton trajectory."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "armadillocudalinearinterpolation_b200", "host")
+LIBDIR = os.path.join(ROOT, "armadillocudalinearinterpolation_b200", "lib")
+Z_DRIVER = np.array([np.float32(0.3310), np.float32(0.6914), np.float32(1.3557)], dtype=np.float64)
+BETA = float(np.float32(13.0589))
+
+
+@pytest.fixture(scope="module")
+def host():
+    subprocess.check_call(["make", "-C", HOST, "-j4"], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(LIBDIR, "libb200host.so"))
+    lib.b200_host_last_error.restype = C.c_char_p
+    return lib
+
+
+def dp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def newton_quadratic(host, guess, tol=1e-10, max_it=20, eps=1e-7, damping=1.0, use_jac=0):
+    n = len(guess)
+    g = np.array(guess, float); sol = np.zeros(n); hist = np.full(max_it + 1, np.nan)
+    nh = C.c_int(); calls = C.c_int(); J = np.zeros((n, n), order="F")
+    rc = host.b200_host_newton_quadratic(n, dp(g), C.c_double(tol), max_it, C.c_double(eps), C.c_double(damping),
+                                         use_jac, dp(sol), dp(hist), C.byref(nh), C.byref(calls), dp(J))
+    assert rc >= 0, host.b200_host_last_error()
+    return dict(sol=sol, hist=hist[:nh.value], its=rc // 4, converged=bool(rc & 2), post_once=bool(rc & 1),
+                calls=calls.value, J=J)
+
+
+def test_newton_converges_quadratically_and_counts_calls(host):
+    r = newton_quadratic(host, [1.0, 1.0, 1.0])
+    assert r["converged"] and r["post_once"]
+    u = r["sol"]
+    F = u ** 2 - np.arange(2, 5) + 0.1 * np.roll(u, -1)
+    assert np.max(np.abs(F)) < 1e-10
+    assert len(r["hist"]) == r["its"] + 1 and r["hist"][-1] <= 1e-10        # history trimmed to the iterations done
+    assert r["hist"][-1] < r["hist"][-2] ** 1.5                              # super-linear tail
+    # reference cost model: 1 + its * (n + 1) evaluations with the solver's own FD loop (NewtonSolver.cpp:67,110,191)
+    assert r["calls"] == 1 + r["its"] * 4
+    rj = newton_quadratic(host, [1.0, 1.0, 1.0], use_jac=1)                  # user Jacobian: 1 + its evaluations
+    assert rj["calls"] == 1 + rj["its"] and np.allclose(rj["sol"], u, atol=1e-9)
+    assert np.allclose(rj["J"], r["J"], atol=1e-5)                           # pJacobianExternal hands out the last Jacobian
+
+
+def test_newton_not_converged_and_damping(host):
+    r = newton_quadratic(host, [1.0, 1.0, 1.0], max_it=2)
+    assert not r["converged"] and r["its"] == 2 and len(r["hist"]) == 3 and r["post_once"]
+    d = newton_quadratic(host, [1.0, 1.0, 1.0], damping=0.5, max_it=60, tol=1e-8)
+    assert d["converged"] and d["its"] > r["its"]
+
+
+@pytest.mark.parametrize("n", [3, 8, 40, 200])
+def test_shim_solve_and_eig_gen_match_numpy(host, n):
+    rng = np.random.default_rng(n)
+    A = np.asfortranarray(rng.standard_normal((n, n)))
+    b = rng.standard_normal(n); x = np.zeros(n)
+    assert host.b200_host_solve(n, dp(A), dp(b), dp(x)) == 0
+    assert np.allclose(x, np.linalg.solve(A, b), rtol=1e-9, atol=1e-9)
+    re = np.zeros(n); im = np.zeros(n)
+    cnt = host.b200_host_stability_linear(n, dp(A), 1, C.c_double(1e-6), 1, dp(re), dp(im))
+    lam = np.linalg.eigvals(A)
+    mine = np.sort_complex(re + 1j * im); ref = np.sort_complex(lam)
+    assert np.allclose(mine, ref, rtol=1e-8, atol=1e-8)
+    assert cnt == int(np.sum(np.abs(lam) > 1.0))
+    assert host.b200_host_solve(2, dp(np.zeros((2, 2), order="F")), dp(np.ones(2)), dp(np.zeros(2))) == 1  # singular
+
+
+def test_stability_problem_types(host):
+    """flow counts Re > 0; map counts |lambda| > 1; equationFree adds I to the FD Jacobian of F = A u - u."""
+    A = np.asfortranarray(np.diag([1.5, 0.5, -0.2]) + 0.01 * np.ones((3, 3)))
+    re = np.zeros(3); im = np.zeros(3)
+    # via the problem: F(u) = A u - u, J = A - I (FD, exact for a linear map up to rounding)
+    assert host.b200_host_stability_linear(3, dp(A), 2, C.c_double(1e-6), 0, dp(re), dp(im)) == 1   # eig(A): one > 1
+    assert np.allclose(np.sort(re), np.sort(np.linalg.eigvals(A).real), atol=1e-6)
+    lamJ = np.linalg.eigvals(A - np.eye(3))
+    assert host.b200_host_stability_linear(3, dp(A), 1, C.c_double(1e-6), 0, None, None) == int(np.sum(np.abs(lamJ) > 1)) == 1  # |eig(A - I)| > 1
+    assert host.b200_host_stability_linear(3, dp(A), 0, C.c_double(1e-6), 0, None, None) == 1       # Re eig(A - I) > 0: one
+    assert host.b200_host_stability_linear(3, dp(A), 0, C.c_double(1e-6), 1, None, None) == 2       # matrix overload on A itself
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Driver.cu"), reason="reference tree not present")
+def test_reference_driver_compiles_unmodified_against_the_host_layer(tmp_path, host):
+    """Drop-in evidence: the reference's own Driver.cu (copied to a temp dir, never into the repo)
+    compiles and links against this host layer + compat headers without a single edit."""
+    src = tmp_path / "Driver_ref.cpp"
+    shutil.copy("/root/reference/Driver.cu", src)
+    exe = tmp_path / "ref_driver"
+    cmd = ["/usr/bin/g++", "-std=c++14", "-O0", f"-I{HOST}/compat", f"-I{HOST}/arma_shim", f"-I{HOST}",
+           f"-I{ROOT}/include", str(src)] + [os.path.join(HOST, f) for f in
+           ("AbstractNonlinearSolver.cpp", "NewtonSolver.cpp", "Stability.cpp", "EventDrivenMapB200.cpp")] + \
+          [f"-L{LIBDIR}", "-lb200edm", f"-Wl,-rpath,{LIBDIR}", "-o", str(exe)]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert exe.exists()
+
+
+@pytest.mark.gpu
+def test_edm_newton_through_the_reference_interfaces(host, oracle):
+    """NewtonSolver drives EventDrivenMapB200 (a) through ComputeF only — the reference's sequential
+    FD loop — and (b) through ComputeDFDU — one batched launch.  Same iterates, bit for bit, and the
+    fixed point the oracle's Newton finds (Driver.cu settings: tol 1e-4, eps 1e-2, <= 10 iterations)."""
+    R, N, n = 8, 1024, 3
+    res = []
+    for mode in (0, 1):
+        sol = np.zeros(n); hist = np.full(11, np.nan); nh = C.c_int(); J = np.zeros((n, n), order="F")
+        rc = host.b200_host_edm_newton(C.c_double(BETA), R, N, dp(Z_DRIVER), n, C.c_double(1e-4), 10, C.c_double(1e-2),
+                                       mode, C.c_double(0.0), dp(sol), dp(hist), C.byref(nh), dp(J))
+        assert rc >= 0, host.b200_host_last_error()
+        res.append((rc, sol, hist[:nh.value], J))
+    assert res[0][0] == 1 and res[1][0] == 1
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][3], res[1][3])
+    # oracle Newton with the same settings
+    cfg = oracle.edm_cfg(R=1, N=N)
+    z = Z_DRIVER.copy(); f, _ = oracle.edm_compute_f(cfg, z, aux=False); hist = [np.linalg.norm(f)]
+    while hist[-1] > 1e-4 and len(hist) <= 10:
+        Jo, f0 = oracle.edm_compute_dfdu(cfg, z, 1e-2)
+        z = z + np.linalg.solve(Jo, -f0); f, _ = oracle.edm_compute_f(cfg, z, aux=False); hist.append(np.linalg.norm(f))
+    assert len(hist) == len(res[1][2])
+    assert np.allclose(res[1][1], z, rtol=0, atol=1e-8)        # FD Jacobians amplify 1e-13 by 1/eps per step
+    assert np.allclose(res[1][2], hist, rtol=1e-5, atol=1e-9)
+    assert np.max(np.abs(res[1][3] - Jo)) < 1e-7 * np.max(np.abs(Jo))
+
+
+@pytest.mark.gpu
+def test_edm_stability_through_the_reference_interfaces(host, oracle):
+    R, N, n = 4, 1024, 3
+    u = np.array([0.33144403, 0.69563678, 1.36572108])
+    out = []
+    for mode in (0, 1):
+        re = np.zeros(n); im = np.zeros(n)
+        cnt = host.b200_host_edm_stability(C.c_double(BETA), R, N, dp(u), n, C.c_double(1e-2), mode, dp(re), dp(im))
+        assert cnt >= 0, host.b200_host_last_error()
+        out.append((cnt, re.copy(), im.copy()))
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+    Jo, _ = oracle.edm_compute_dfdu(oracle.edm_cfg(R=1, N=N), u, 1e-2)
+    lam = np.linalg.eigvals(Jo + np.eye(3))
+    assert out[1][0] == int(np.sum(np.abs(lam) > 1.0)) == 1
+    assert np.allclose(np.sort(out[1][1]), np.sort(lam.real), atol=1e-6)
