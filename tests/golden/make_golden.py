@@ -93,7 +93,8 @@ def edm_cases():
     run("hetero_sigma0.5", z_driver, R=4, N=1024, sigma=0.5, seed=42)
     run("perturbed_c", [z_driver[0] + 1e-2, z_driver[1], z_driver[2]], R=1, N=1024)
     run("two_fronts", z_driver[:2], R=1, N=512, M=2)
-    run("four_fronts", z_driver + [2.05], R=1, N=1024, M=4)
+    run("four_fronts", z_driver + [2.2], R=1, N=1024, M=4)
+    run("four_fronts_quiet", z_driver + [2.05], R=1, N=1024, M=4)   # ring goes quiet: not accepted, F = NaN
     run("short_horizon", z_driver, R=1, N=1024, time_horizon=1.0)
     run("quirk_accept0", z_driver, R=3, N=256, quirks=1)
     # the survey's independent emulation values for the two emulation cases
