@@ -29,6 +29,7 @@
 // `decision` predicate (EventDrivenMap.cu:559) is provably false.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -50,6 +51,40 @@ template <> struct M<float> {
   static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
   static __device__ __forceinline__ float nan_() { return __int_as_float(0x7fc00000); }
 };
+
+// ---- short-latency FP64 exp / divide for the event loop ----
+// The loop's critical path is a serial Newton chain (divide -> two exps -> f, df) run by a
+// handful of lanes while the rest of the CTA waits at a barrier, so what matters is the length of
+// the dependent-instruction chain, not instruction count.  exp(x) = 2^(k/64) * exp(r) with a
+// 64-entry table of 2^(j/64) in shared memory and a degree-5 polynomial in Estrin form
+// (|r| <= ln2/128, truncation 3.5e-17): ~10 dependent operations instead of ~30, about 1 ulp.
+// Division uses MUFU.RCP64H + two Newton steps + one residual correction (no IEEE fix-up path).
+__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
+  if (!(fabs(x) < 690.0)) return exp(x);  // overflow / underflow / NaN: library path
+  const double t = fma(x, 92.33248261689366, 6755399441055744.0);  // 64/ln2, round-to-nearest magic
+  const int k = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -0x1.62e42fee00000p-7, x);    // ln2/64, high 32 bits (kd * hi is exact)
+  r = fma(kd, -0x1.a39ef35793c76p-39, r);           // ln2/64, low part
+  const double r2 = r * r;
+  const double a = fma(r, 1.0 / 6.0, 0.5);
+  const double b = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  const double q = fma(r2, fma(r2, b, a), r);          // exp(r) - 1
+  const double tj = tab[k & 63];
+  const double m = fma(tj, q, tj);
+  const int e = k >> 6;
+  return __hiloint2double(__double2hiint(m) + (e << 20), __double2loint(m));
+}
+__device__ __forceinline__ float fast_exp(float x, const float*) { return expf(x); }
+__device__ __forceinline__ double fast_div(double a, double b) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+  y = fma(y, fma(-b, y, 1.0), y);
+  y = fma(y, fma(-b, y, 1.0), y);
+  const double q = a * y;
+  return fma(fma(-q, b, a), y, q);
+}
+__device__ __forceinline__ float fast_div(float a, float b) { return a / b; }
 
 // model constants in the arithmetic type of the run (parameters.hpp:1-15)
 template <typename T>
@@ -204,31 +239,45 @@ edm_prepare_kernel(Consts<T> k, unsigned N, unsigned Mf, T beta, const double* _
 }
 
 // ---------------------------------------------------------------- evolve ----
-// Exact event time of one neuron: `decision` predicate + Newton from t = 0
-// (eventTime/fun/dfun, EventDrivenMap.cu:544-573).  Returns 100 when the neuron cannot fire.
+// `decision` predicate of eventTime (EventDrivenMap.cu:559), evaluated exactly as written.
 template <typename T>
-__device__ __forceinline__ T exact_event_time(const Consts<T>& k, T v, T s, T beta, unsigned& its) {
+__device__ __forceinline__ bool exact_decision(const Consts<T>& k, T v, T s, T beta) {
   const T one = (T)1;
   const T r = s / (k.vth - k.I);
   const T p = M<T>::pow_(r, one / beta);
-  const bool decision = v > k.vth * p + k.I * (one - p) - (k.vth - k.I) / (beta - one) * (r - p);
-  if (!decision) return (T)100;
+  return v > k.vth * p + k.I * (one - p) - (k.vth - k.I) / (beta - one) * (r - p);
+}
+
+// Newton from t = 0 on the closed-form membrane solution (fun/dfun/eventTime,
+// EventDrivenMap.cu:544-573): same iterates, same stopping test as the reference.
+template <typename T>
+__device__ __forceinline__ T newton_event_time(const Consts<T>& k, T v, T s, T beta, const T* etab,
+                                               unsigned& its) {
+  const T one = (T)1;
+  const T i1mb = fast_div(one, one - beta), ibm1 = -i1mb;
   T t = (T)0;
   T f = v - k.vth;         // fun(0)  : exp(0) = 1 makes every other term exactly 0
   T df = (k.I - v) + s;    // dfun(0)
   unsigned counter = 0;
   while (((double)fabs(f) > k.tol) && (counter < k.counter_max)) {
-    t -= f / df;
-    const T e1 = M<T>::exp_(-t);
-    const T e2 = M<T>::exp_((one - beta) * t);
-    f = v * e1 + k.I * (one - e1) + s * e1 / (one - beta) * (e2 - one) - k.vth;
-    df = k.I * e1 - v * e1 + s * e1 * e2 + (s * e1 * (e2 - one)) / (beta - one);
+    t -= fast_div(f, df);
+    const T e1 = fast_exp(-t, etab);
+    const T e2 = fast_exp((one - beta) * t, etab);
+    const T se1 = s * e1;
+    f = v * e1 + k.I * (one - e1) + se1 * i1mb * (e2 - one) - k.vth;
+    df = k.I * e1 - v * e1 + se1 * e2 + (se1 * (e2 - one)) * ibm1;
     counter++;
   }
   its += counter;
   T out = fabs(t);
   if (out != out) out = (T)100;  // Q5: a NaN event time never wins the arg-min
   return out;
+}
+
+template <typename T>
+__device__ __forceinline__ T exact_event_time(const Consts<T>& k, T v, T s, T beta, const T* etab, unsigned& its) {
+  if (!exact_decision<T>(k, v, s, beta)) return (T)100;
+  return newton_event_time<T>(k, v, s, beta, etab, its);
 }
 
 // order-preserving integer key of a non-negative, non-NaN time
@@ -277,20 +326,27 @@ struct EvolveArgs {
   unsigned long long* counters;  // [4]: events, candidates (filter survivors), newton its, fallbacks (nullable)
 };
 
+// The candidate list holds at most kCandCap neurons (typically ~10 survive the filter); if more
+// do, the event is resolved by the exact block-wide pass instead.
+constexpr unsigned kCandCap = 256;
+__host__ __device__ inline unsigned cand_cap(unsigned N) { return N < kCandCap ? N : kCandCap; }
+
 template <typename T>
 __host__ __device__ inline size_t evolve_smem_bytes(unsigned N, unsigned Mf, bool het) {
   size_t b = 0;
+  const unsigned cap = cand_cap(N);
   b += sizeof(T) * N;                       // bw / w
-  b += sizeof(T) * N * (het ? 3 : 2);       // cand_v, cand_s, (cand_b)
-  b += sizeof(int) * N;                     // cand_i
+  b += sizeof(T) * cap * (het ? 3 : 2);     // cand_v, cand_s, (cand_b)
+  b += sizeof(int) * cap;                   // cand_i
   b += (sizeof(T) * 2 + sizeof(int) * 2 + 4) * Mf;  // front bookkeeping
+  b += sizeof(T) * 64;                      // exp table
   b += 256;                                 // scalars + alignment slack
   b += 32 * 16;                             // per-warp partial results
   return b;
 }
 
-template <typename T, int NPT, bool HET, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+template <typename T, int NPT, bool HET, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 edm_evolve_kernel(const EvolveArgs<T> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned N = A.N, Mf = A.Mf;
@@ -299,17 +355,19 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   // ---- shared memory carve-up ----
   unsigned char* sp = smem_raw;
   T* bw = reinterpret_cast<T*>(sp); sp += sizeof(T) * N;            // w[d] (x beta when homogeneous)
-  T* cand_v = reinterpret_cast<T*>(sp); sp += sizeof(T) * N;
-  T* cand_s = reinterpret_cast<T*>(sp); sp += sizeof(T) * N;
+  const unsigned cap = cand_cap(N);
+  T* cand_v = reinterpret_cast<T*>(sp); sp += sizeof(T) * cap;
+  T* cand_s = reinterpret_cast<T*>(sp); sp += sizeof(T) * cap;
   T* cand_b = nullptr;
-  if (HET) { cand_b = reinterpret_cast<T*>(sp); sp += sizeof(T) * N; }
+  if (HET) { cand_b = reinterpret_cast<T*>(sp); sp += sizeof(T) * cap; }
   T* last_t = reinterpret_cast<T*>(sp); sp += sizeof(T) * Mf;
   T* cross_t = reinterpret_cast<T*>(sp); sp += sizeof(T) * Mf;
+  T* etab = reinterpret_cast<T*>(sp); sp += sizeof(T) * 64;         // 2^(j/64) for fast_exp
   sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
   unsigned long long* wkey = reinterpret_cast<unsigned long long*>(sp); sp += 8 * 32;
   EventMsg<T>* ev = reinterpret_cast<EventMsg<T>*>(sp); sp += ((sizeof(EventMsg<T>) + 15) / 16) * 16;
   unsigned long long* fb_key = reinterpret_cast<unsigned long long*>(sp); sp += 8;
-  int* cand_i = reinterpret_cast<int*>(sp); sp += sizeof(int) * N;
+  int* cand_i = reinterpret_cast<int*>(sp); sp += sizeof(int) * cap;
   int* last_i = reinterpret_cast<int*>(sp); sp += sizeof(int) * Mf;
   int* cross_i = reinterpret_cast<int*>(sp); sp += sizeof(int) * Mf;
   unsigned* widx = reinterpret_cast<unsigned*>(sp); sp += 4 * 32;
@@ -346,10 +404,12 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   const T h_ibm1 = one / (hb - one);
   const T h_i1mb = one / (one - hb);
   const bool h_filt = hb >= (T)1.5;
+  const float h_invb32 = (float)(one / hb);
   const T inv_vmI = one / (k.vth - k.I);
   const T vmI = k.vth - k.I;
 
   for (unsigned d = tid; d < N; d += nthr) bw[d] = HET ? A.w[d] : hb * A.w[d];
+  if (tid < 64) etab[tid] = (T)exp2((double)tid * (1.0 / 64.0));
   if (tid == 0) {
     ncand[0] = 0; ncand[1] = 0;
     for (unsigned m = 0; m < Mf; ++m) {
@@ -367,8 +427,8 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
 
   // Conservative candidate test.  The reference's predicate is
   //   v > vth p + I (1-p) - (vth-I)/(beta-1) (r - p),  r = s/(vth-I), p = r^(1/beta),
-  // i.e. g := (v - vth) - (vth-I) * ((beta p - r)/(beta-1) - 1) > 0.  p is evaluated with the
-  // MUFU lg2/ex2 units (relative error < 2e-6); the neuron is dropped only when g is below
+  // i.e. g := (v - vth) - (vth-I) * ((beta p - r)/(beta-1) - 1) > 0.  Stage 2 evaluates p with
+  // the MUFU lg2/ex2 units (relative error < 2e-6); the neuron is dropped only when g is below
   // -1e-4 (1 + p), orders of magnitude more than that error can move it.
   auto scan = [&](int parity) {
 #pragma unroll
@@ -378,20 +438,30 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       const T b = HET ? bt[q] : hb;
       const bool fo = HET ? filt[q] : h_filt;
       const T rr = s[q] * inv_vmI;
-      bool maybe;
+      bool maybe, certain = false;
       if (!fo) maybe = true;
       else if (rr > (T)0) {
-        if (rr > (T)1e-30 && rr < (T)1e30) {
-          const float p32 = exp2f(__log2f((float)rr) * (float)(one / b));
+        // stage 1: p >= 1 when r >= 1 and p >= r when r < 1 bound g from above with two FP64
+        // operations; whole warps far from the fronts leave here without touching the MUFU path
+        const T d1 = v[q] - k.vth;
+        const T g_ub = (rr >= one) ? d1 + (s[q] - vmI) * (HET ? ibm1[q] : h_ibm1) : (d1 - s[q]) + vmI;
+        if (g_ub < (T)-1e-9) maybe = false;
+        else if (rr > (T)1e-30 && rr < (T)1e30) {
+          const float p32 = exp2f(__log2f((float)rr) * (HET ? (float)(one / b) : h_invb32));
           const T p = (T)p32;
           const T g = (v[q] - k.vth) - vmI * ((b * p - rr) * (HET ? ibm1[q] : h_ibm1) - one);
-          maybe = !(g < (T)-1e-4 * (one + p));
+          const T margin = (T)1e-4 * (one + p);
+          maybe = !(g < -margin);
+          certain = g > margin;   // the predicate is provably true: no pow() needed either
         } else maybe = true;
       } else maybe = (rr == (T)0);  // r < 0 or NaN: pow() is NaN, the predicate is false
       if (maybe) {
         const int slot = atomicAdd(&ncand[parity], 1);
-        cand_v[slot] = v[q]; cand_s[slot] = s[q]; cand_i[slot] = (int)j;
-        if (HET) cand_b[slot] = b;
+        if (slot < (int)cap) {
+          cand_v[slot] = v[q]; cand_s[slot] = s[q];
+          cand_i[slot] = (int)j | (certain ? (int)0x80000000 : 0);
+          if (HET) cand_b[slot] = b;
+        }
       }
     }
   };
@@ -416,11 +486,11 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     m.dt = dt; m.idx = idx; m.cont = cont; m.fallback = 0;
     m.e1 = m.cA = m.cB = m.e12 = (T)0;
     if (cont) {
-      const T e1 = M<T>::exp_(-dt);
+      const T e1 = fast_exp(-dt, etab);
       m.e1 = e1;
       m.cA = k.I * (one - e1);
       if (!HET) {
-        const T e2 = M<T>::exp_((one - hb) * dt);
+        const T e2 = fast_exp((one - hb) * dt, etab);
         m.cB = e1 * h_i1mb * (e2 - one);
         m.e12 = e1 * e2;
       }
@@ -432,7 +502,9 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   scan(parity);
   for (;;) {
     __syncthreads();  // B1: candidate list of this event is complete
-    const int n = ncand[parity];
+    const int n_found = ncand[parity];
+    const bool overflow = n_found > (int)cap;   // block-uniform: resolve this event exactly
+    const int n = overflow ? 0 : n_found;
     if (tid == 0) ncand[parity ^ 1] = 0;
     // ---- exact event times of the candidates, compacted into the first warps ----
     const unsigned long long kInf = ~0ull;
@@ -440,10 +512,14 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     unsigned bidx = 0xffffffffu;
     for (int c = (int)tid; c < n; c += (int)nthr) {
       unsigned its = 0;
-      const T tc = exact_event_time<T>(k, cand_v[c], cand_s[c], HET ? cand_b[c] : hb, its);
+      const int ci = cand_i[c];
+      const T cb = HET ? cand_b[c] : hb;
+      const T cv = cand_v[c], cs = cand_s[c];
+      T tc = (T)100;
+      if (ci < 0 || exact_decision<T>(k, cv, cs, cb)) tc = newton_event_time<T>(k, cv, cs, cb, etab, its);
       if (A.counters) stat_newton += its;
       const unsigned long long kc = time_key(tc);
-      const unsigned ic = (unsigned)cand_i[c];
+      const unsigned ic = (unsigned)(ci & 0x7fffffff);
       if (kc < key || (kc == key && ic < bidx)) { key = kc; bidx = ic; }
     }
     const bool multi = n > 32;  // block-uniform
@@ -485,7 +561,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
         keys[q] = kInf;
         if (j < N) {
           unsigned its = 0;
-          keys[q] = time_key(exact_event_time<T>(k, v[q], s[q], HET ? bt[q] : hb, its));
+          keys[q] = time_key(exact_event_time<T>(k, v[q], s[q], HET ? bt[q] : hb, etab, its));
           if (keys[q] < mk) mk = keys[q];
         }
       }
@@ -518,7 +594,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       const unsigned dist = (j >= m.idx) ? (j - m.idx) : (m.idx - j);
       if (HET) {
         const T b = bt[q];
-        const T e2 = M<T>::exp_((one - b) * m.dt);
+        const T e2 = fast_exp((one - b) * m.dt, etab);
         const T cB = m.e1 * (-ibm1[q]) * (e2 - one);
         T vn = v[q] * m.e1 + (m.cA + s[q] * cB);
         v[q] = (j == m.idx) ? (T)0 : vn;
@@ -780,14 +856,19 @@ int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaSt
   if (threads > 1024) return fail(B200_ERR_UNSUPPORTED, "no_neurons=%u needs more than 1024 threads at %d neurons/thread", h->N, NPT);
   const size_t smem = evolve_smem_bytes<T>(h->N, h->Mf, HET);
   if (smem > 227 * 1024) return fail(B200_ERR_UNSUPPORTED, "no_neurons=%u / no_fronts=%u need %zu B of shared memory (max 232448)", h->N, h->Mf, smem);
-  if (threads <= 256) {
-    auto kern = edm_evolve_kernel<T, NPT, HET, 256>;
+  auto go = [&](auto kern) -> int {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)nitems, threads, smem, st>>>(A);
+    return B200_OK;
+  };
+  // 128-thread CTAs capped at 64 registers: 8 rings resident per SM, i.e. 8 serial Newton
+  // chains overlapping (measured: 5.9 -> 4.5 ms per default evaluation vs 4 rings at 118 regs)
+  if (threads <= 128) {
+    B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8>));
+  } else if (threads <= 256) {
+    B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 256, 2>));
   } else {
-    auto kern = edm_evolve_kernel<T, NPT, HET, 1024>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)nitems, threads, smem, st>>>(A);
+    B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 1024, 1>));
   }
   B200_CUDA(cudaGetLastError());
   return B200_OK;

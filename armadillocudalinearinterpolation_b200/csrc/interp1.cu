@@ -130,7 +130,7 @@ int plan1_create(b200_interp1_plan* p, const T* xg, const T* yg, size_t ng) {
   B200_CUDA(cudaStreamCreateWithFlags(&p->stream[1], cudaStreamNonBlocking));
   B200_CUDA(cudaEventCreateWithFlags(&p->ev[0], cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&p->ev[1], cudaEventDisableTiming));
-  B200_TRY(axis_create<T>(axis_of<T>(p), xg, ng, p->stream[0], "interp1 grid"));
+  B200_TRY(axis_create<T>(axis_of<T>(p), xg, ng, p->stream[0], "interp1 grid", true));
   B200_CUDA(cudaMalloc(&p->yg, ng * sizeof(T)));
   B200_CUDA(cudaMalloc(&p->seg, ng * 4 * sizeof(T)));
   B200_CUDA(cudaMemcpyAsync(p->yg, yg, ng * sizeof(T), cudaMemcpyHostToDevice, p->stream[0]));
