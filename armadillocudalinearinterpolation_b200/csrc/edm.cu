@@ -297,10 +297,9 @@ __device__ __forceinline__ void warp_argmin(unsigned long long& key, unsigned& i
 }
 
 template <typename T>
-struct EventMsg {       // written by the finalising thread, read by everybody after the barrier
+struct EventMsg {       // written by thread 0 after the arg-min, read by everybody after the barrier
   T dt, e1, cA, cB, e12;  // event-uniform advance coefficients (cB, e12: homogeneous ensemble)
   unsigned idx;
-  int cont;             // 1: advance and continue, 0: stop
   int fallback;         // 1: nobody can fire within 100 time units -> block-wide exact pass
 };
 
@@ -345,7 +344,7 @@ __host__ __device__ inline size_t evolve_smem_bytes(unsigned N, unsigned Mf, boo
   return b;
 }
 
-template <typename T, int NPT, bool HET, int MAXT, int MINB>
+template <typename T, int NPT, bool HET, int MAXT, int MINB, bool FULL>
 __global__ void __launch_bounds__(MAXT, MINB)
 edm_evolve_kernel(const EvolveArgs<T> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -373,6 +372,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   unsigned* widx = reinterpret_cast<unsigned*>(sp); sp += 4 * 32;
   int* ncand = reinterpret_cast<int*>(sp); sp += 8;                 // [2], double buffered
   unsigned* fb_idx = reinterpret_cast<unsigned*>(sp); sp += 4;
+  int* stop = reinterpret_cast<int*>(sp); sp += 4;
   unsigned char* crossed = sp;                                      // [Mf]
 
   const unsigned long long item = A.item_begin + blockIdx.x;
@@ -411,7 +411,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   for (unsigned d = tid; d < N; d += nthr) bw[d] = HET ? A.w[d] : hb * A.w[d];
   if (tid < 64) etab[tid] = (T)exp2((double)tid * (1.0 / 64.0));
   if (tid == 0) {
-    ncand[0] = 0; ncand[1] = 0;
+    ncand[0] = 0; ncand[1] = 0; *stop = 0;
     for (unsigned m = 0; m < Mf; ++m) {
       last_i[m] = A.init_index[(size_t)col * Mf + m];  // EventDrivenMap.cu:595-599
       last_t[m] = (T)0;                                // Q4
@@ -434,7 +434,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
 #pragma unroll
     for (int q = 0; q < NPT; ++q) {
       const unsigned j = tid + q * nthr;
-      if (j >= N) continue;
+      if (!FULL && j >= N) continue;
       const T b = HET ? bt[q] : hb;
       const bool fo = HET ? filt[q] : h_filt;
       const T rr = s[q] * inv_vmI;
@@ -466,36 +466,46 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     }
   };
 
-  // Bookkeeping of one event by the finalising thread (EventDrivenMap.cu:620-643) and the
-  // event-uniform advance coefficients for everybody else.
-  auto finalise = [&](T dt, unsigned idx) {
-    t_now += dt;
+  // The event message: (dt, idx) and the event-uniform advance coefficients.
+  auto publish = [&](T dt, unsigned idx) {
+    EventMsg<T> m;
+    m.dt = dt; m.idx = idx; m.fallback = 0;
+    const T e1 = fast_exp(-dt, etab);
+    m.e1 = e1;
+    m.cA = k.I * (one - e1);
+    m.cB = m.e12 = (T)0;
+    if (!HET) {
+      const T e2 = fast_exp((one - hb) * dt, etab);
+      m.cB = e1 * h_i1mb * (e2 - one);
+      m.e12 = e1 * e2;
+    }
+    *ev = m;
+  };
+
+  // Bookkeeping of one event (EventDrivenMap.cu:620-643): which front it belongs to, last-before-T
+  // / first-after-T records, loop condition (:601).  It runs one event LATE, on a thread of a warp
+  // that would otherwise idle at the barrier while warp 0 runs the next Newton chain; the event
+  // that was speculatively resolved meanwhile is simply dropped when the loop condition fails
+  // (the state after the last event is never read).
+  const unsigned bk_tid = (nwarps > 1) ? 32u : 0u;
+  bool pending = false;
+  T pend_dt = (T)0;
+  unsigned pend_idx = 0;
+  auto bookkeep = [&]() {
+    t_now += pend_dt;
     n_events++;
+    const int idx = (int)pend_idx;
     unsigned mi = 0;
     for (unsigned i = 1; i < Mf; ++i) {  // literal `minIndex += (closer)` — SURVEY Q14
-      const int di = abs((int)idx - last_i[i]);
-      const int dm = abs((int)idx - last_i[mi]);
+      const int di = abs(idx - last_i[i]);
+      const int dm = abs(idx - last_i[mi]);
       mi += (unsigned)(di < dm);
     }
     if (!crossed[mi]) {
-      if (t_now > k.T_end) { cross_t[mi] = t_now; cross_i[mi] = (int)idx; crossed[mi] = 1; n_crossed++; }
-      else { last_t[mi] = t_now; last_i[mi] = (int)idx; }
+      if (t_now > k.T_end) { cross_t[mi] = t_now; cross_i[mi] = idx; crossed[mi] = 1; n_crossed++; }
+      else { last_t[mi] = t_now; last_i[mi] = idx; }
     }
-    const int cont = (n_crossed < Mf) && (t_now < 2 * k.T_end);  // :601
-    EventMsg<T> m;
-    m.dt = dt; m.idx = idx; m.cont = cont; m.fallback = 0;
-    m.e1 = m.cA = m.cB = m.e12 = (T)0;
-    if (cont) {
-      const T e1 = fast_exp(-dt, etab);
-      m.e1 = e1;
-      m.cA = k.I * (one - e1);
-      if (!HET) {
-        const T e2 = fast_exp((one - hb) * dt, etab);
-        m.cB = e1 * h_i1mb * (e2 - one);
-        m.e12 = e1 * e2;
-      }
-    }
-    *ev = m;
+    if (!((n_crossed < Mf) && (t_now < 2 * k.T_end))) *stop = 1;  // :601
   };
 
   int parity = 0;
@@ -506,6 +516,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     const bool overflow = n_found > (int)cap;   // block-uniform: resolve this event exactly
     const int n = overflow ? 0 : n_found;
     if (tid == 0) ncand[parity ^ 1] = 0;
+    if (tid == bk_tid && pending) bookkeep();
     // ---- exact event times of the candidates, compacted into the first warps ----
     const unsigned long long kInf = ~0ull;
     unsigned long long key = kInf;
@@ -539,7 +550,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       // the smallest-index neuron at 100 and must be found by the exact block-wide pass
       if (n == 0 || key >= time_key((T)100)) {
         EventMsg<T> m;
-        m.dt = m.e1 = m.cA = m.cB = m.e12 = (T)0; m.idx = 0; m.cont = 1; m.fallback = 1;
+        m.dt = m.e1 = m.cA = m.cB = m.e12 = (T)0; m.idx = 0; m.fallback = 1;
         *ev = m;
         *fb_key = kInf; *fb_idx = 0xffffffffu;
         stat_fb++;
@@ -547,10 +558,11 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
         T dt;
         if (sizeof(T) == 8) dt = (T)__longlong_as_double((long long)key);
         else dt = (T)__uint_as_float((unsigned)key);
-        finalise(dt, bidx);
+        publish(dt, bidx);
       }
     }
-    __syncthreads();  // B2: event message visible
+    __syncthreads();  // B2: event message and the (late) loop condition are visible
+    if (*stop) break;
     if (ev->fallback) {
       // exact pass over every neuron (rare: the ring has gone quiet)
       unsigned long long mk = kInf;
@@ -578,30 +590,31 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
         T dt;
         if (sizeof(T) == 8) dt = (T)__longlong_as_double((long long)gk);
         else dt = (T)__uint_as_float((unsigned)gk);
-        finalise(dt, *fb_idx);
+        publish(dt, *fb_idx);
       }
       __syncthreads();
     }
     const EventMsg<T> m = *ev;
-    if (!m.cont) break;
+    if (tid == bk_tid) { pending = true; pend_dt = m.dt; pend_idx = m.idx; }
     // ---- advance every neuron to the event, reset the firing one, deliver the kick
     //      (EventDrivenMap.cu:612-618), then test who can fire next ----
     parity ^= 1;
+    const int rel0 = (int)tid - (int)m.idx;
 #pragma unroll
     for (int q = 0; q < NPT; ++q) {
       const unsigned j = tid + q * nthr;
-      if (j >= N) continue;
-      const unsigned dist = (j >= m.idx) ? (j - m.idx) : (m.idx - j);
+      if (!FULL && j >= N) continue;
+      const unsigned dist = (unsigned)abs(rel0 + q * (int)nthr);
       if (HET) {
         const T b = bt[q];
         const T e2 = fast_exp((one - b) * m.dt, etab);
         const T cB = m.e1 * (-ibm1[q]) * (e2 - one);
         T vn = v[q] * m.e1 + (m.cA + s[q] * cB);
-        v[q] = (j == m.idx) ? (T)0 : vn;
+        v[q] = (dist == 0) ? (T)0 : vn;
         s[q] = s[q] * (m.e1 * e2) + b * bw[dist];
       } else {
         T vn = v[q] * m.e1 + (m.cA + s[q] * m.cB);
-        v[q] = (j == m.idx) ? (T)0 : vn;
+        v[q] = (dist == 0) ? (T)0 : vn;
         s[q] = s[q] * m.e12 + bw[dist];
       }
     }
@@ -610,7 +623,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
 
   // ---- epilogue: restriction by two-point linear interpolation in time
   //      (RestrictKernel, EventDrivenMap.cu:769-785) and the accept flag (:669-672) ----
-  if (tid == 0) {
+  if (tid == bk_tid) {
     const size_t o = (size_t)blockIdx.x;
     for (unsigned m = 0; m < Mf; ++m) {
       const T t0 = last_t[m], t1 = cross_t[m];
@@ -626,11 +639,11 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     }
     A.accept[o] = (n_crossed == Mf) ? 1 : 0;
     A.event_count[o] = n_events;
-    if (A.counters) {
-      atomicAdd(&A.counters[0], (unsigned long long)n_events);
-      atomicAdd(&A.counters[1], (unsigned long long)stat_cand);
-      atomicAdd(&A.counters[3], (unsigned long long)stat_fb);
-    }
+    if (A.counters) atomicAdd(&A.counters[0], (unsigned long long)n_events);
+  }
+  if (tid == 0 && A.counters) {
+    atomicAdd(&A.counters[1], (unsigned long long)stat_cand);
+    atomicAdd(&A.counters[3], (unsigned long long)stat_fb);
   }
   if (A.counters) {
     // Newton iterations were counted by whichever thread ran them
@@ -863,12 +876,14 @@ int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaSt
   };
   // 128-thread CTAs capped at 64 registers: 8 rings resident per SM, i.e. 8 serial Newton
   // chains overlapping (measured: 5.9 -> 4.5 ms per default evaluation vs 4 rings at 118 regs)
+  const bool full = (h->N == threads * (unsigned)NPT);  // no ragged tail: bounds checks compiled out
   if (threads <= 128) {
-    B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8>));
+    if (full) B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8, true>));
+    else B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8, false>));
   } else if (threads <= 256) {
-    B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 256, 2>));
+    B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 256, 2, false>));
   } else {
-    B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 1024, 1>));
+    B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 1024, 1, false>));
   }
   B200_CUDA(cudaGetLastError());
   return B200_OK;

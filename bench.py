@@ -58,47 +58,63 @@ def make_grid():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md), through
+    NVML (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints):
+    the timed region lasts tens of milliseconds, too short for an `nvidia-smi -lms` process."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.t = index, [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # CUDA_VISIBLE_DEVICES remaps indices; resolve through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.h = h
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((sm, mx, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.nv:
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        sm = [r[0] for r in self.rows]
+        reasons = set()
         for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if val.lower().startswith("active"):
+            for bit, name in self.REASONS.items():
+                if r[2] & bit:
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(r[1] for r in self.rows)) if sm else None,
+                "power_w_max": max((r[3] for r in self.rows), default=None), "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def cpu_threads():
@@ -211,6 +227,9 @@ def main():
     B.set_device(local)
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line (NCCL prints its version banner there otherwise)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_
         dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_
@@ -263,6 +282,7 @@ def main():
                        "grid": "4096x4096 float64 column-major (128 MiB), seed 2234",
                        "queries": "1e8 (x,y) ~ U[0,1]^2 per GPU, unsorted, seed 2235+rank",
                        "l2": "inputs larger than L2 (1.6 GB of queries + 0.8 GB of outputs per step)",
+                       "layout": "axes staged in shared memory by TMA bulk copy; Z as 2x2 corner records (512 MiB)",
                        "parallelism": f"query shards x{n_gpus}, no collective"},
             "gpu_launches": args.steps,
             "clocks": clocks,
@@ -270,7 +290,7 @@ def main():
                     "ms_per_step": e2e_ms, "api": "b200_interp2_scattered (pinned host buffers, 2-slot chunked pipeline)",
                     "max_abs_diff_vs_device_path": check},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "interp2_scattered_vec_kernel<double>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "interp2_scattered_smem_kernel<double, cells>",
                          "algorithmic_bytes_per_launch": alg_bytes}}
 
     # ---------------- secondary workloads ----------------
