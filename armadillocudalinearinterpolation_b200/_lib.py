@@ -59,3 +59,17 @@ def set_device(i):
 
 def synchronize():
     check(lib().b200_synchronize())
+
+
+def bench_random_gather(table_bytes=512 << 20, n_gathers=100_000_000):
+    """Machine ceiling for random 32-byte gathers (returns ms, gathers/s)."""
+    ms, rate = C.c_double(), C.c_double()
+    check(lib().b200_bench_random_gather(C.c_size_t(table_bytes), C.c_size_t(n_gathers), C.byref(ms), C.byref(rate)))
+    return ms.value, rate.value
+
+
+def bench_fp64_fma():
+    """Dense FP64 FMA ceiling of the current device in TFLOP/s."""
+    t = C.c_double()
+    check(lib().b200_bench_fp64_fma(C.byref(t)))
+    return t.value

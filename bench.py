@@ -274,6 +274,13 @@ def main():
     check = float(np.abs(hzn[:1000] - zq[:1000].cpu().numpy()).max())
     del hx, hy, hz
 
+    # machine ceiling for this access pattern, measured live: independent 32-byte gathers from a
+    # 512 MiB table (every L2 miss fills a 128-byte line on B200, so uniformly random queries are
+    # bounded by this, not by the streaming copy rate)
+    from armadillocudalinearinterpolation_b200 import _lib as L_
+    g_ms, g_rate = L_.bench_random_gather(512 << 20, NQ)
+    fp64_peak = L_.bench_fp64_fma()
+
     line = {"metric": "interp points/s (2-D bilinear, 4096x4096 f64 grid, 1e8 scattered queries)",
             "value": value, "unit": "points/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -291,7 +298,10 @@ def main():
                     "max_abs_diff_vs_device_path": check},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "interp2_scattered_smem_kernel<double, cells>",
-                         "algorithmic_bytes_per_launch": alg_bytes}}
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "random_gather_ceiling": {"gathers_per_s": g_rate, "ms_for_1e8": g_ms,
+                                                   "frac_of_ceiling": (NQ / (ms_per_step * 1e-3)) / g_rate,
+                                                   "note": "1e8 independent 32-byte gathers from a 512 MiB table, same GPU, same run"}}}
 
     # ---------------- secondary workloads ----------------
     if not args.no_extra:
@@ -333,6 +343,18 @@ def main():
         gb = (8 * 1e8 + ALG_BYTES_GRID + 16 * 1e4) / (msg * 1e-3) / 1e9
         extra["interp2_grid_f64_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msg * 1e-3), "ms_per_launch": msg,
                                              "algorithmic_GBps": gb, "roofline_frac": gb / peak}
+        # configs[1] with tile-sorted queries (SURVEY 8d variant iii): same points, ordered by grid cell
+        cell = (xq * (NX - 1)).floor().to(torch.int64) * NY + (yq * (NY - 1)).floor().to(torch.int64)
+        order = cell.argsort()
+        del cell
+        xs, ys = xq[order], yq[order]
+        del order
+        nst = max(5, args.steps // 2)
+        mss = time_steps(torch, lambda: plan.scattered(xs, ys, out=zq), nst, 3, dist) / nst
+        gbs = alg_bytes / (mss * 1e-3) / 1e9
+        extra["interp2_scattered_f64_cell_sorted_queries"] = {"points_per_s": n_gpus * NQ / (mss * 1e-3), "ms_per_launch": mss,
+                                                              "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+        del xs, ys
         # configs[2]: one map evaluation, parameters.hpp default ensemble (R=1000, N=1024, M=3, T=5)
         for sigma in (0.0, 0.5):
             m = B.EventDrivenMap([BETA], 1000, noNeurons=1024)
@@ -350,7 +372,8 @@ def main():
             extra[f"map_eval_R1000_N1024_sigma{sigma}"] = {
                 "evals_per_s_per_gpu": 1e3 / call_ms, "ms_per_compute_f": call_ms, "evolve_kernel_ms": float(np.mean(evolve_ms)),
                 "events": cnt["events"], "neuron_event_updates_per_s": cnt["events"] * 1024 / (np.mean(evolve_ms) * 1e-3),
-                "candidates": cnt["candidates"], "newton_its": cnt["newton_its"]}
+                "candidates": cnt["candidates"], "newton_its": cnt["newton_its"],
+                "fp64_fma_peak_tflops_measured": fp64_peak}
             m.close()
         # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
         # items sharded over the ranks, positions gathered with one NCCL all-gather

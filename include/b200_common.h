@@ -51,6 +51,13 @@ int b200_host_free(void* ptr);
 /* Block until all work queued by this library on the current device is complete. */
 int b200_synchronize(void);
 
+/* ---- bench introspection: machine ceilings measured live (not part of the hot path) ----
+ * Independent 32-byte record gathers from a table of `table_bytes` (choose >> L2): time of the
+ * best of 3 timed passes and gathers per second.  On B200 each miss fills a 128-byte line. */
+int b200_bench_random_gather(size_t table_bytes, size_t n_gathers, double* ms_out, double* gathers_per_s);
+/* Dense FP64 FMA issue ceiling of the current device, in TFLOP/s (2 flops per FMA). */
+int b200_bench_fp64_fma(double* tflops_out);
+
 #ifdef __cplusplus
 }
 #endif
