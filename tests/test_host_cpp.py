@@ -149,3 +149,17 @@ def test_edm_stability_through_the_reference_interfaces(host, oracle):
     lam = np.linalg.eigvals(Jo + np.eye(3))
     assert out[1][0] == int(np.sum(np.abs(lam) > 1.0)) == 1
     assert np.allclose(np.sort(out[1][1]), np.sort(lam.real), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_continuation_driver_runs(host):
+    """examples/driver.cpp — the reference experiment plus the beta-continuation loop the reference
+    leaves commented out (Driver.cu:86-112): Newton converges at each beta and the travelling wave has
+    exactly one unstable direction (the spectrum pinned in tests/test_oracle_edm.py)."""
+    exe = os.path.join(LIBDIR, "driver_b200")
+    out = subprocess.run([exe, "2", "16", "1024", "0.1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("beta =")]
+    assert len(lines) == 2
+    assert all("unstable eigenvalues = 1" in l for l in lines), lines
+    assert out.stdout.count("The method converged after") == 2
