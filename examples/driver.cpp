@@ -46,8 +46,9 @@ int main(int argc, char* argv[]) {
     newton.Solve(solution, history, flag);
     const int unstable = stability.ComputeNumUnstableEigenvalues(solution);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    std::cout << "beta = " << parameters(0) << "  solution = " << solution.t()
-              << "  unstable eigenvalues = " << unstable << (unstable > 0 ? "  (unstable)" : "  (stable)")
+    std::cout << "beta = " << parameters(0) << "  solution =";
+    for (arma::uword j = 0; j < solution.n_elem; ++j) std::cout << " " << solution(j);
+    std::cout << "  unstable eigenvalues = " << unstable << (unstable > 0 ? "  (unstable)" : "  (stable)")
               << "  [" << ms << " ms]" << std::endl;
     parameters += dbeta;                                   // Driver.cu:107-109
     map.SetParameters(0, (float)parameters(0));
