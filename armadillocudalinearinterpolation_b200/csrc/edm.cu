@@ -238,6 +238,64 @@ edm_prepare_kernel(Consts<T> k, unsigned N, unsigned Mf, T beta, const double* _
   }
 }
 
+// ---------------------------------------------------------------- profile map helpers ----
+// Periodic linear interpolation on the ring grid X[i] = -L + (2L/n) i (X[n] = L carries y[0]) with the
+// interp1 rule (w = |X[a]-x| / (|X[a]-x| + |X[b]-x|), (1-w) y[a] + w y[b]); every operation individually
+// rounded so that the lifted / restricted profiles equal the CPU restatement bit for bit.
+template <typename T>
+__device__ __forceinline__ T periodic_interp(const T* __restrict__ y, unsigned n, T L, T x) {
+  const T h = div_rn(mul_rn((T)2, L), (T)n);
+  long long a = (long long)div_rn(add_rn(x, L), h);
+  a = max(0ll, min(a, (long long)n - 1));
+  while (a > 0 && add_rn(-L, mul_rn(h, (T)a)) > x) --a;
+  while (a + 1 <= (long long)n - 1 && add_rn(-L, mul_rn(h, (T)(a + 1))) <= x) ++a;
+  const T xa = add_rn(-L, mul_rn(h, (T)a));
+  const T xb = (a + 1 == (long long)n) ? L : add_rn(-L, mul_rn(h, (T)(a + 1)));
+  const T ya = y[a], yb = y[(a + 1) % n];
+  const T ea = fabs(sub_rn(xa, x)), eb = fabs(sub_rn(xb, x));
+  const T w = (ea > (T)0) ? div_rn(ea, add_rn(ea, eb)) : (T)0;
+  return add_rn(mul_rn(sub_rn((T)1, w), ya), mul_rn(w, yb));
+}
+
+// Lift of the profile map: coarse (V_c, S_c) -> neurons, one CTA per column; neurons lifted at or above
+// threshold start from reset, as in LiftKernel (EventDrivenMap.cu:540).
+template <typename T>
+__global__ void __launch_bounds__(256)
+edm_profile_lift_kernel(Consts<T> k, unsigned N, unsigned nc, const double* __restrict__ u_cols,
+                        T* __restrict__ uc_scratch, T* __restrict__ lift_v, T* __restrict__ lift_s) {
+  const unsigned col = blockIdx.x;
+  const double* u = u_cols + (size_t)col * 2 * nc;
+  T* uc = uc_scratch + (size_t)col * 2 * nc;   // the column in the arithmetic type of the run
+  for (unsigned i = threadIdx.x; i < 2 * nc; i += blockDim.x) uc[i] = (T)u[i];
+  __syncthreads();
+  for (unsigned j = threadIdx.x; j < N; j += blockDim.x) {
+    const T x = add_rn(-k.L, mul_rn((T)(2 * k.L / N), (T)j));
+    T v = periodic_interp<T>(uc, nc, k.L, x);
+    v *= (T)(v < (T)1);
+    lift_v[(size_t)col * N + j] = v;
+    lift_s[(size_t)col * N + j] = periodic_interp<T>(uc + nc, nc, k.L, x);
+  }
+}
+
+// Mean over accepted realisations in a fixed order, F = mean - u.  One thread per (column, entry).
+template <typename T>
+__global__ void __launch_bounds__(256)
+edm_profile_reduce_kernel(unsigned R, unsigned n, size_t ncols, const double* __restrict__ u_cols,
+                          const T* __restrict__ restricted, const int32_t* __restrict__ accept,
+                          double* __restrict__ f_cols) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ncols * n) return;
+  const size_t col = g / n;
+  const unsigned m = (unsigned)(g % n);
+  const T* base = restricted + col * R * n + m;
+  const int32_t* acc = accept + col * R;
+  T sum = (T)0;
+  unsigned count = 0;
+  for (unsigned r = 0; r < R; ++r)
+    if (acc[r] == 1) { sum += base[(size_t)r * n]; ++count; }
+  f_cols[g] = (double)(sum / count) - u_cols[g];
+}
+
 // ---------------------------------------------------------------- evolve ----
 // `decision` predicate of eventTime (EventDrivenMap.cu:559), evaluated exactly as written.
 template <typename T>
@@ -301,6 +359,7 @@ struct EventMsg {       // written by thread 0 after the arg-min, read by everyb
   T dt, e1, cA, cB, e12;  // event-uniform advance coefficients (cB, e12: homogeneous ensemble)
   unsigned idx;
   int fallback;         // 1: nobody can fire within 100 time units -> block-wide exact pass
+  int last;             // profile map: final event-free advance to the horizon
 };
 
 template <typename T>
@@ -323,6 +382,7 @@ struct EvolveArgs {
   T* last_time;
   T* crossed_time;
   unsigned long long* counters;  // [4]: events, candidates (filter survivors), newton its, fallbacks (nullable)
+  unsigned profile_nc;   // 0: front map (the reference); > 0: profile map on profile_nc coarse knots
 };
 
 // The candidate list holds at most kCandCap neurons (typically ~10 survive the filter); if more
@@ -331,8 +391,8 @@ constexpr unsigned kCandCap = 256;
 __host__ __device__ inline unsigned cand_cap(unsigned N) { return N < kCandCap ? N : kCandCap; }
 
 template <typename T>
-__host__ __device__ inline size_t evolve_smem_bytes(unsigned N, unsigned Mf, bool het) {
-  size_t b = 0;
+__host__ __device__ inline size_t evolve_smem_bytes(unsigned N, unsigned Mf, bool het, bool profile = false) {
+  size_t b = profile ? 2 * sizeof(T) * N : 0;   // fine state staged for the restriction
   const unsigned cap = cand_cap(N);
   b += sizeof(T) * N;                       // bw / w
   b += sizeof(T) * cap * (het ? 3 : 2);     // cand_v, cand_s, (cand_b)
@@ -373,7 +433,10 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   int* ncand = reinterpret_cast<int*>(sp); sp += 8;                 // [2], double buffered
   unsigned* fb_idx = reinterpret_cast<unsigned*>(sp); sp += 4;
   int* stop = reinterpret_cast<int*>(sp); sp += 4;
-  unsigned char* crossed = sp;                                      // [Mf]
+  unsigned char* crossed = sp; sp += Mf;                            // [Mf]
+  sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
+  T* sv = reinterpret_cast<T*>(sp);                                 // profile map only: [N] + [N]
+  T* ss = sv + N;
 
   const unsigned long long item = A.item_begin + blockIdx.x;
   const unsigned col = (unsigned)(item / A.R), r = (unsigned)(item % A.R);
@@ -409,7 +472,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   const T vmI = k.vth - k.I;
 
   for (unsigned d = tid; d < N; d += nthr) bw[d] = HET ? A.w[d] : hb * A.w[d];
-  if (tid < 64) etab[tid] = (T)exp2((double)tid * (1.0 / 64.0));
+  for (unsigned i = tid; i < 64; i += nthr) etab[i] = (T)exp2((double)i * (1.0 / 64.0));
   if (tid == 0) {
     ncand[0] = 0; ncand[1] = 0; *stop = 0;
     for (unsigned m = 0; m < Mf; ++m) {
@@ -467,8 +530,19 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   };
 
   // The event message: (dt, idx) and the event-uniform advance coefficients.
+  const bool prof = A.profile_nc != 0;
+  int prof_ok = 1;
   auto publish = [&](T dt, unsigned idx) {
     EventMsg<T> m;
+    m.last = 0;
+    if (prof) {
+      // profile map: evolve for exactly T; the event that would overshoot becomes a plain advance
+      if (!(t_now + dt <= k.T_end)) { m.last = 1; dt = k.T_end - t_now; }
+      else {
+        t_now += dt;
+        if (++n_events >= 64 * (int)N) { prof_ok = 0; *stop = 1; }
+      }
+    }
     m.dt = dt; m.idx = idx; m.fallback = 0;
     const T e1 = fast_exp(-dt, etab);
     m.e1 = e1;
@@ -550,7 +624,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       // the smallest-index neuron at 100 and must be found by the exact block-wide pass
       if (n == 0 || key >= time_key((T)100)) {
         EventMsg<T> m;
-        m.dt = m.e1 = m.cA = m.cB = m.e12 = (T)0; m.idx = 0; m.fallback = 1;
+        m.dt = m.e1 = m.cA = m.cB = m.e12 = (T)0; m.idx = 0; m.fallback = 1; m.last = 0;
         *ev = m;
         *fb_key = kInf; *fb_idx = 0xffffffffu;
         stat_fb++;
@@ -595,7 +669,17 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       __syncthreads();
     }
     const EventMsg<T> m = *ev;
-    if (tid == bk_tid) { pending = true; pend_dt = m.dt; pend_idx = m.idx; }
+    if (tid == bk_tid && !prof) { pending = true; pend_dt = m.dt; pend_idx = m.idx; }
+    if (m.last) {  // profile map: no spike, no kick; the state at exactly T is the result
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) {
+        const T e2 = HET ? fast_exp((one - bt[q]) * m.dt, etab) : (T)0;
+        const T cB = HET ? m.e1 * (-ibm1[q]) * (e2 - one) : m.cB;
+        v[q] = v[q] * m.e1 + (m.cA + s[q] * cB);
+        s[q] = s[q] * (HET ? m.e1 * e2 : m.e12);
+      }
+      break;
+    }
     // ---- advance every neuron to the event, reset the firing one, deliver the kick
     //      (EventDrivenMap.cu:612-618), then test who can fire next ----
     parity ^= 1;
@@ -623,7 +707,32 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
 
   // ---- epilogue: restriction by two-point linear interpolation in time
   //      (RestrictKernel, EventDrivenMap.cu:769-785) and the accept flag (:669-672) ----
-  if (tid == bk_tid) {
+  if (prof) {
+    // restriction of the profile map: the fine state at time T, sampled back at the coarse knots
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) {
+      const unsigned j = tid + q * nthr;
+      if (j < N) { sv[j] = v[q]; ss[j] = s[q]; }
+    }
+    __syncthreads();
+    const unsigned nc = A.profile_nc;
+    T* out = A.position + (size_t)blockIdx.x * 2 * nc;
+    for (unsigned i = tid; i < nc; i += nthr) {
+      const T x = add_rn(-k.L, mul_rn((T)(2 * k.L / nc), (T)i));
+      out[i] = periodic_interp<T>(sv, N, k.L, x);
+      out[nc + i] = periodic_interp<T>(ss, N, k.L, x);
+    }
+    if (tid == 0) {
+      A.accept[blockIdx.x] = prof_ok;
+      A.event_count[blockIdx.x] = n_events;
+      if (A.counters) {
+        atomicAdd(&A.counters[0], (unsigned long long)n_events);
+        atomicAdd(&A.counters[1], (unsigned long long)stat_cand);
+        atomicAdd(&A.counters[3], (unsigned long long)stat_fb);
+      }
+    }
+  } else if (tid == bk_tid) {
     const size_t o = (size_t)blockIdx.x;
     for (unsigned m = 0; m < Mf; ++m) {
       const T t0 = last_t[m], t1 = cross_t[m];
@@ -641,7 +750,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     A.event_count[o] = n_events;
     if (A.counters) atomicAdd(&A.counters[0], (unsigned long long)n_events);
   }
-  if (tid == 0 && A.counters) {
+  if (tid == 0 && A.counters && !prof) {
     atomicAdd(&A.counters[1], (unsigned long long)stat_cand);
     atomicAdd(&A.counters[3], (unsigned long long)stat_fb);
   }
@@ -724,6 +833,8 @@ struct b200_edm {
   double sigma = 0.0;
   uint64_t seed = 42;
   int debug = 0, timing = 0, npt = 0;
+  uint32_t profile_nc = 0;   // 0: front map; > 0: profile map on this many coarse knots
+  void* d_uc = nullptr;      // profile map: columns converted to the run's arithmetic type
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_up = nullptr, ev_done = nullptr;
@@ -764,6 +875,8 @@ struct b200_edm {
 namespace {
 
 size_t esize(const b200_edm* h) { return h->prec == B200_F64 ? 8 : 4; }
+// length of the coarse vector: fronts (reference map) or 2 x coarse knots (profile map)
+size_t ndim(const b200_edm* h) { return h->profile_nc ? 2 * (size_t)h->profile_nc : (size_t)h->Mf; }
 
 template <typename T>
 Consts<T> make_consts(const b200_edm* h) {
@@ -780,6 +893,7 @@ void free_ensemble(b200_edm* h) {
   h->w_dirty = h->beta_dirty = true;
 }
 void free_batch(b200_edm* h) {
+  cudaFree(h->d_uc); h->d_uc = nullptr;
   cudaFree(h->d_z); cudaFree(h->d_f); cudaFree(h->d_mean); cudaFree(h->d_init); cudaFree(h->d_lv);
   cudaFree(h->d_ls); cudaFree(h->d_pos); cudaFree(h->d_accept); cudaFree(h->d_evcount);
   cudaFree(h->d_last_i); cudaFree(h->d_cross_i); cudaFree(h->d_last_t); cudaFree(h->d_cross_t);
@@ -798,10 +912,13 @@ int ensure_pinned(b200_edm* h, size_t doubles) {
 }
 
 int ensure_batch(b200_edm* h, size_t ncols, size_t nitems) {
-  const size_t es = esize(h), N = h->N, Mf = h->Mf;
+  const size_t es = esize(h), N = h->N, Mf = ndim(h);
+  const bool prof = h->profile_nc != 0;
   if (ncols > h->cap_cols) {
     cudaFree(h->d_z); cudaFree(h->d_f); cudaFree(h->d_mean); cudaFree(h->d_init); cudaFree(h->d_lv); cudaFree(h->d_ls);
+    cudaFree(h->d_uc); h->d_uc = nullptr;
     h->d_z = h->d_f = h->d_mean = nullptr; h->d_init = nullptr; h->d_lv = h->d_ls = nullptr; h->cap_cols = 0;
+    if (prof) B200_CUDA(cudaMalloc(&h->d_uc, ncols * Mf * es));
     B200_CUDA(cudaMalloc(&h->d_z, ncols * Mf * sizeof(double)));
     B200_CUDA(cudaMalloc(&h->d_f, ncols * Mf * sizeof(double)));
     B200_CUDA(cudaMalloc(&h->d_mean, ncols * Mf * sizeof(double)));
@@ -818,10 +935,12 @@ int ensure_batch(b200_edm* h, size_t ncols, size_t nitems) {
     B200_CUDA(cudaMalloc(&h->d_pos, nitems * Mf * es));
     B200_CUDA(cudaMalloc(&h->d_accept, nitems * sizeof(int32_t)));
     B200_CUDA(cudaMalloc(&h->d_evcount, nitems * sizeof(int32_t)));
-    B200_CUDA(cudaMalloc(&h->d_last_i, nitems * Mf * sizeof(int32_t)));
-    B200_CUDA(cudaMalloc(&h->d_cross_i, nitems * Mf * sizeof(int32_t)));
-    B200_CUDA(cudaMalloc(&h->d_last_t, nitems * Mf * es));
-    B200_CUDA(cudaMalloc(&h->d_cross_t, nitems * Mf * es));
+    if (!prof) {  // front records exist only for the reference map
+      B200_CUDA(cudaMalloc(&h->d_last_i, nitems * Mf * sizeof(int32_t)));
+      B200_CUDA(cudaMalloc(&h->d_cross_i, nitems * Mf * sizeof(int32_t)));
+      B200_CUDA(cudaMalloc(&h->d_last_t, nitems * Mf * es));
+      B200_CUDA(cudaMalloc(&h->d_cross_t, nitems * Mf * es));
+    }
     h->cap_items = nitems;
   }
   if (!h->d_clamped) B200_CUDA(cudaMalloc(&h->d_clamped, sizeof(int32_t)));
@@ -855,8 +974,6 @@ int ensure_ensemble(b200_edm* h, cudaStream_t st) {
 int pick_npt(const b200_edm* h) {
   if (h->npt > 0) return h->npt;
   const unsigned N = h->N;
-  if (N <= 128) return 1;
-  if (N <= 256) return 2;
   if (N <= 512) return 4;
   if (N <= 2048) return 8;
   return 16;
@@ -867,7 +984,7 @@ int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaSt
   unsigned threads = (h->N + NPT - 1) / NPT;
   threads = (threads + 31) / 32 * 32;
   if (threads > 1024) return fail(B200_ERR_UNSUPPORTED, "no_neurons=%u needs more than 1024 threads at %d neurons/thread", h->N, NPT);
-  const size_t smem = evolve_smem_bytes<T>(h->N, h->Mf, HET);
+  const size_t smem = evolve_smem_bytes<T>(h->N, A.Mf, HET, h->profile_nc != 0);
   if (smem > 227 * 1024) return fail(B200_ERR_UNSUPPORTED, "no_neurons=%u / no_fronts=%u need %zu B of shared memory (max 232448)", h->N, h->Mf, smem);
   auto go = [&](auto kern) -> int {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -892,12 +1009,10 @@ int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaSt
 template <typename T, bool HET>
 int launch_evolve(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaStream_t st) {
   switch (pick_npt(h)) {
-    case 1: return launch_evolve_npt<T, 1, HET>(h, A, nitems, st);
-    case 2: return launch_evolve_npt<T, 2, HET>(h, A, nitems, st);
     case 4: return launch_evolve_npt<T, 4, HET>(h, A, nitems, st);
     case 8: return launch_evolve_npt<T, 8, HET>(h, A, nitems, st);
     case 16: return launch_evolve_npt<T, 16, HET>(h, A, nitems, st);
-    default: return fail(B200_ERR_INVALID_ARG, "neurons per thread must be 1, 2, 4, 8 or 16");
+    default: return fail(B200_ERR_INVALID_ARG, "neurons per thread must be 4, 8 or 16");
   }
 }
 
@@ -905,6 +1020,12 @@ int launch_evolve(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaStream
 template <typename T>
 int run_prepare(b200_edm* h, size_t ncols, cudaStream_t st) {
   B200_CUDA(cudaMemsetAsync(h->d_clamped, 0, sizeof(int32_t), st));
+  if (h->profile_nc) {
+    edm_profile_lift_kernel<T><<<(unsigned)ncols, 256, 0, st>>>(make_consts<T>(h), h->N, h->profile_nc, h->d_z,
+                                                                (T*)h->d_uc, (T*)h->d_lv, (T*)h->d_ls);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+  }
   const size_t smem = sizeof(FrontCoef<T>) * h->Mf;
   if (smem > 200 * 1024) return fail(B200_ERR_UNSUPPORTED, "no_fronts=%u too large for the lift kernel", h->Mf);
   auto kern = edm_prepare_kernel<T>;
@@ -920,7 +1041,8 @@ template <typename T>
 int run_evolve(b200_edm* h, size_t item_begin, size_t item_end, T* pos, int32_t* accept, cudaStream_t st) {
   EvolveArgs<T> A;
   A.k = make_consts<T>(h);
-  A.N = h->N; A.R = h->R; A.Mf = h->Mf;
+  A.N = h->N; A.R = h->R; A.Mf = h->profile_nc ? 0 : h->Mf;
+  A.profile_nc = h->profile_nc;
   A.beta_mean = (T)h->params[0];
   A.beta = (h->sigma != 0.0) ? (const T*)h->beta : nullptr;
   A.w = (const T*)h->w;
@@ -928,7 +1050,7 @@ int run_evolve(b200_edm* h, size_t item_begin, size_t item_end, T* pos, int32_t*
   A.init_index = h->d_init;
   A.item_begin = item_begin;
   A.position = pos; A.accept = accept; A.event_count = h->d_evcount;
-  A.last_index = h->d_last_i; A.crossed_index = h->d_cross_i;
+  A.last_index = h->profile_nc ? nullptr : h->d_last_i; A.crossed_index = h->d_cross_i;
   A.last_time = (T*)h->d_last_t; A.crossed_time = (T*)h->d_cross_t;
   A.counters = (h->debug || h->timing) ? h->d_counters : nullptr;
   const size_t nitems = item_end - item_begin;
@@ -944,6 +1066,12 @@ int run_evolve(b200_edm* h, size_t item_begin, size_t item_end, T* pos, int32_t*
 
 template <typename T>
 int run_reduce(b200_edm* h, size_t ncols, const T* pos, const int32_t* accept, double* f_cols, cudaStream_t st) {
+  if (h->profile_nc) {
+    const size_t n = ndim(h), total = ncols * n;
+    edm_profile_reduce_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->R, (unsigned)n, ncols, h->d_z, pos, accept, f_cols);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+  }
   edm_reduce_kernel<T><<<(unsigned)ncols, 256, 0, st>>>(h->R, h->Mf, (double)(T)h->model.time_horizon,
                                                         h->model.quirks, h->d_z, pos, accept, f_cols, h->d_mean);
   B200_CUDA(cudaGetLastError());
@@ -969,10 +1097,12 @@ int check_handle(const b200_edm* h, const char* fn) {
 }
 
 int upload_z(b200_edm* h, const double* z_cols, size_t n, size_t ncols, cudaStream_t st) {
-  if (n != h->Mf) return fail(B200_ERR_INVALID_ARG, "vector length %zu != no_fronts %u", n, h->Mf);
-  for (size_t c = 0; c < ncols; ++c)
-    if (!(z_cols[c * n] == z_cols[c * n]) || z_cols[c * n] == 0.0)
-      return fail(B200_ERR_INVALID_ARG, "column %zu: wave speed z[0] must be finite and non-zero", c);
+  if (n != ndim(h))
+    return fail(B200_ERR_INVALID_ARG, "vector length %zu != %s %zu", n, h->profile_nc ? "2 x coarse knots" : "no_fronts", ndim(h));
+  if (!h->profile_nc)
+    for (size_t c = 0; c < ncols; ++c)
+      if (!(z_cols[c * n] == z_cols[c * n]) || z_cols[c * n] == 0.0)
+        return fail(B200_ERR_INVALID_ARG, "column %zu: wave speed z[0] must be finite and non-zero", c);
   // the pinned staging block is reused: wait for the previous upload to have left it
   if (h->up_pending) { B200_CUDA(cudaEventSynchronize(h->ev_up)); h->up_pending = false; }
   B200_TRY(ensure_pinned(h, 2 * n * ncols));
@@ -1131,11 +1261,17 @@ int b200_edm_new_seed(b200_edm* h) {
   h->beta_dirty = true;
   return B200_OK;
 }
+int b200_edm_set_profile_mode(b200_edm* h, uint32_t n_coarse) {
+  B200_TRY(check_handle(h, "edm_set_profile_mode"));
+  if (n_coarse == 1) return fail(B200_ERR_INVALID_ARG, "profile map needs at least 2 coarse knots (0 switches it off)");
+  if (n_coarse != h->profile_nc) { cudaSetDevice(h->device); free_batch(h); h->profile_nc = n_coarse; h->last_cols = 0; }
+  return B200_OK;
+}
+
 int b200_edm_set_tuning(b200_edm* h, int neurons_per_thread) {
   B200_TRY(check_handle(h, "edm_set_tuning"));
-  if (neurons_per_thread != 0 && neurons_per_thread != 1 && neurons_per_thread != 2 &&
-      neurons_per_thread != 4 && neurons_per_thread != 8 && neurons_per_thread != 16)
-    return fail(B200_ERR_INVALID_ARG, "neurons per thread must be 0 (auto), 1, 2, 4, 8 or 16");
+  if (neurons_per_thread != 0 && neurons_per_thread != 4 && neurons_per_thread != 8 && neurons_per_thread != 16)
+    return fail(B200_ERR_INVALID_ARG, "neurons per thread must be 0 (auto), 4, 8 or 16");
   h->npt = neurons_per_thread;
   return B200_OK;
 }
@@ -1154,7 +1290,7 @@ int b200_edm_compute_f(b200_edm* h, const double* z, size_t n, double* f_out) {
 int b200_edm_compute_dfdu(b200_edm* h, const double* u, size_t n, double eps, double* jac_out, double* f0_out) {
   B200_TRY(check_handle(h, "edm_compute_dfdu"));
   if (!u || !jac_out) return fail(B200_ERR_INVALID_ARG, "edm_compute_dfdu: NULL argument");
-  if (n != h->Mf) return fail(B200_ERR_INVALID_ARG, "vector length %zu != no_fronts %u", n, h->Mf);
+  if (n != ndim(h)) return fail(B200_ERR_INVALID_ARG, "vector length %zu != problem dimension %zu", n, ndim(h));
   if (!(eps != 0.0)) return fail(B200_ERR_INVALID_ARG, "finite-difference epsilon must be non-zero");
   // columns 0..n-1: u + eps e_i (NewtonSolver.cpp:184-188), column n: u
   std::vector<double> zc((n + 1) * n), fc((n + 1) * n);
@@ -1193,7 +1329,7 @@ int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     B200_TRY(run_prepare<float>(h, ncols, st));
     B200_TRY(run_evolve<float>(h, item_begin, item_end, (float*)h->d_pos, accept_dev, st));
     if (nitems)
-      convert_kernel<float, double><<<(unsigned)((nitems * h->Mf + 255) / 256), 256, 0, st>>>((const float*)h->d_pos, pos_dev, nitems * h->Mf);
+      convert_kernel<float, double><<<(unsigned)((nitems * ndim(h) + 255) / 256), 256, 0, st>>>((const float*)h->d_pos, pos_dev, nitems * ndim(h));
     B200_CUDA(cudaGetLastError());
   }
   h->last_cols = ncols;
@@ -1218,7 +1354,7 @@ int b200_edm_reduce_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     // accumulated in float exactly as the single-GPU path does
     const size_t nitems = ncols * h->R;
     B200_TRY(ensure_batch(h, ncols, nitems));
-    convert_kernel<double, float><<<(unsigned)((nitems * h->Mf + 255) / 256), 256, 0, st>>>(pos_all_dev, (float*)h->d_pos, nitems * h->Mf);
+    convert_kernel<double, float><<<(unsigned)((nitems * ndim(h) + 255) / 256), 256, 0, st>>>(pos_all_dev, (float*)h->d_pos, nitems * ndim(h));
     B200_TRY(run_reduce<float>(h, ncols, (const float*)h->d_pos, accept_all_dev, f_cols_dev, st));
   }
   return mark_done(h, st);
@@ -1270,7 +1406,11 @@ int b200_edm_debug_fetch(b200_edm* h, b200_edm_debug_what what, void* out, size_
   if (!h->debug) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: debug flag is off (SetDebugFlag)");
   if (h->last_cols == 0) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: no evaluation has run yet");
   B200_CUDA(cudaSetDevice(h->device));
-  const size_t C = h->last_cols, R = h->R, N = h->N, Mf = h->Mf, es = esize(h);
+  const size_t C = h->last_cols, R = h->R, N = h->N, Mf = ndim(h), es = esize(h);
+  if (h->profile_nc && what != B200_EDM_DBG_LIFT_V && what != B200_EDM_DBG_LIFT_S && what != B200_EDM_DBG_ACCEPT &&
+      what != B200_EDM_DBG_POSITION && what != B200_EDM_DBG_EVENT_COUNT && what != B200_EDM_DBG_BETA &&
+      what != B200_EDM_DBG_COUPLING)
+    return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: array %d does not exist for the profile map", (int)what);
   const void* src = nullptr;
   size_t count = 0;
   bool real = false, is_int = false;

@@ -43,6 +43,7 @@ class EventDrivenMap:
                                       C.c_uint32(noFronts), B200_F64 if precision == "f64" else B200_F32,
                                       C.byref(self._h)))
         self.R, self.N, self.M = int(noReal), int(noNeurons), int(noFronts)
+        self._fronts = int(noFronts)
         self._last_cols = 0
 
     # ---- AbstractNonlinearProblem (AbstractNonlinearProblem.hpp:11-13) ----
@@ -138,6 +139,12 @@ class EventDrivenMap:
         for k, v in kw.items():
             setattr(m, k, v)
         check(self._L.b200_edm_set_model(self._h, C.byref(m)))
+
+    def SetProfileMode(self, n_coarse):
+        """Switch to the profile map on n_coarse coarse knots (vectors of length 2 n_coarse); 0 = front map."""
+        check(self._L.b200_edm_set_profile_mode(self._h, C.c_uint32(n_coarse)))
+        self.M = 2 * int(n_coarse) if n_coarse else self._fronts
+        self._last_cols = 0
 
     def SetTuning(self, neurons_per_thread):
         check(self._L.b200_edm_set_tuning(self._h, int(neurons_per_thread)))

@@ -44,6 +44,8 @@ class EventDrivenMapB200 : public AbstractNonlinearProblem, public AbstractNonli
   // additions
   void SetFiniteDifferenceEpsilon(double epsilon) { mEpsilon = epsilon; }  // Driver.cu:37 uses 1e-2
   void SetSeed(unsigned long long seed);
+  // profile map (BASELINE config 5, see b200_edm_set_profile_mode): vectors become (V_c, S_c), n = 2 nCoarse
+  void SetProfileMode(unsigned int nCoarse);
   void SetPrintOutput(bool on) { mPrint = on; }
   // n x ncols evaluation points -> n x ncols residuals, one launch
   void ComputeFBatch(const arma::mat& uCols, arma::mat& fCols);

@@ -6,7 +6,10 @@ items; rank g evolves a contiguous slice of the items on its GPU (b200_edm_evolv
 the restricted front positions + accept flags are exchanged with ONE all-gather (NCCL over
 NVLink; a few hundred kB), and every rank forms the masked means in the same fixed order
 (b200_edm_reduce_items_dev) — so the Jacobian is bitwise independent of the number of GPUs.
-Sharding by items rather than by columns keeps all 8 GPUs busy even for n = 3.
+Sharding by items rather than by columns keeps all 8 GPUs busy even for n = 3.  When there are
+many columns (the profile map of BASELINE config 5 has n + 1 = 1001) each rank instead owns a
+contiguous slice of whole columns, reduces them locally and only the residual columns
+(n doubles each) are all-gathered — the exchange shrinks from items x n to ncols x n values.
 """
 import numpy as np
 
@@ -67,8 +70,18 @@ class GpuEngine:
         self.map.ReduceItemsDev(z_cols, pos, acc, f, stream=self._stream())
         return f.cpu().numpy().T  # (n, ncols)
 
-    def empty(self, rows):
-        return self.torch.zeros((rows, self.M + 1), dtype=self.torch.float64, device=self.device)
+    def empty(self, rows, cols=None):
+        return self.torch.zeros((rows, (self.M + 1) if cols is None else cols), dtype=self.torch.float64, device=self.device)
+
+    def columns(self, z_cols, out):
+        """Whole columns on this rank: out[c, :] = F(z_cols[:, c]) (host-buffer batch call)."""
+        if z_cols.shape[1]:
+            f = self.map.ComputeFBatch(z_cols)
+            out[:z_cols.shape[1]] = self.torch.from_numpy(np.ascontiguousarray(f.T)).to(self.device)
+
+    def set_profile_mode(self, n_coarse):
+        self.map.SetProfileMode(n_coarse)
+        self.M = self.map.M
 
 
 class ShardedJacobian:
@@ -78,16 +91,38 @@ class ShardedJacobian:
     to the GPU engine — the CPU tests inject a host engine to exercise the sharding logic with
     the gloo backend."""
 
-    def __init__(self, parameters, noReal, noNeurons=1024, noFronts=3, precision="f64", group=None, engine=None):
+    def __init__(self, parameters, noReal, noNeurons=1024, noFronts=3, precision="f64", group=None, engine=None,
+                 shard="auto"):
         self.dist = group if (group is not None and group.is_initialized()) else None
         self.world = self.dist.get_world_size() if self.dist else 1
         self.rank = self.dist.get_rank() if self.dist else 0
         self.engine = engine or GpuEngine(parameters, noReal, noNeurons, noFronts, precision)
         self.R, self.M = int(noReal), int(noFronts)
+        self.shard = shard  # "items", "columns" or "auto" (columns when there are >= 2 per rank)
+
+    def SetProfileMode(self, n_coarse):
+        self.engine.set_profile_mode(n_coarse)
+        self.M = self.engine.M
+
+    def _columns(self, z_cols):
+        ncols = z_cols.shape[1]
+        per, slices = partition_items(ncols, self.world)
+        lo, hi = slices[self.rank]
+        n = z_cols.shape[0]
+        local = self.engine.empty(per, n)
+        self.engine.columns(np.asfortranarray(z_cols[:, lo:hi]), local)
+        if self.world > 1:
+            gathered = self.engine.empty(per * self.world, n)
+            self.dist.all_gather_into_tensor(gathered, local)
+        else:
+            gathered = local
+        return np.asfortranarray(gathered[:ncols].cpu().numpy().T)
 
     def ComputeFBatch(self, z_cols):
         z_cols = np.asfortranarray(z_cols, np.float64)
         ncols = z_cols.shape[1]
+        if self.shard == "columns" or (self.shard == "auto" and ncols >= 2 * self.world and self.world > 1):
+            return self._columns(z_cols)
         n_items = ncols * self.R
         per, slices = partition_items(n_items, self.world)
         lo, hi = slices[self.rank]

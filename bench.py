@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--config5-full", action="store_true", help="profile-map stability at R = 1000 (1e6 neurons per column)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -385,6 +386,31 @@ def main():
         extra["fd_jacobian_n3_R1000_N1024"] = {"jacobians_per_s": 1e3 / msj, "map_evals_per_s": 4e3 / msj,
                                                "ms_per_jacobian": msj, "ranks": n_gpus, "scaling": "strong",
                                                "collective": "all_gather of (items x 3) positions" if world > 1 else "none"}
+        # configs[4]: stability analysis on a 1e3-dim coarse PROFILE (profile map: n = 2 x 500 knots),
+        # 1001 evaluations per Jacobian; columns sharded over the ranks, residual columns all-gathered.
+        # R = 64 realisations per column by default (--config5-full: R = 1000, i.e. 1e6 neurons per column)
+        fm = B.EventDrivenMap([BETA], 1, noNeurons=1024)
+        fm.SetDebugFlag(True); fm.ComputeF(Z_DRIVER)
+        lv, ls = fm.DebugFetch("lift_v")[0], fm.DebugFetch("lift_s")[0]
+        fm.close()
+        nc = 500
+        xf = -3.0 + 6.0 / 1024 * np.arange(1024); xc = -3.0 + 6.0 / nc * np.arange(nc)
+        u0 = np.concatenate([np.interp(xc, xf, lv), np.interp(xc, xf, ls)])
+        R5 = 1000 if args.config5_full else 64
+        pj = parallel.ShardedJacobian([BETA], R5, noNeurons=1024, group=dist, shard="columns" if world > 1 else "items")
+        pj.engine.map.SetTimeHorizon(1.0)
+        pj.SetProfileMode(nc)
+        J5 = pj.ComputeDFDU(u0, 1e-3)
+        reps5 = 1 if args.config5_full else 3
+        ms5 = wall_steps(torch, lambda: pj.ComputeDFDU(u0, 1e-3), reps5, 0, dist) / reps5
+        t0 = time.perf_counter()
+        lam = np.linalg.eigvals(J5 + np.eye(2 * nc)) if rank == 0 else None
+        eig_ms = 1e3 * (time.perf_counter() - t0)
+        extra[f"profile_stability_n1000_N1024_R{R5}"] = {
+            "ms_per_jacobian": ms5, "map_evals_per_s": 1001e3 / ms5, "columns": 1001, "rings": 1001 * R5,
+            "neurons_per_column": 1024 * R5, "time_horizon": 1.0, "ranks": n_gpus, "scaling": "strong",
+            "unstable_eigenvalues": int(np.sum(np.abs(lam) > 1.0)) if rank == 0 else None,
+            "host_eig_ms": eig_ms, "collective": "all_gather of 1001 residual columns (8 MB)" if world > 1 else "none"}
         line["extra"] = extra
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------

@@ -94,6 +94,20 @@ int b200_edm_compute_f_batch(b200_edm* h, const double* z_cols, size_t n, size_t
 int b200_edm_compute_dfdu(b200_edm* h, const double* u, size_t n, double eps,
                           double* jac_out, double* f0_out);
 
+/* ---- profile map (BASELINE config 5: "1e3-dim coarse profile"; NEW, not in the reference) ----
+ * The reference's coarse variable is 3 numbers (wave speed + front delays, noSpikes in
+ * parameters.hpp:12).  With n_coarse > 0 the same handle instead evaluates the equation-free map on
+ * coarse PROFILES u = (V_c[n_coarse], S_c[n_coarse]) sampled at X_c[i] = -L + (2L/n_coarse) i:
+ *   lift     : linear interpolation (the interp1 rule, periodic ring) of (V_c, S_c) onto the no_neurons
+ *              grid, neurons at/above threshold reset as in LiftKernel (EventDrivenMap.cu:540);
+ *   evolve   : the reference's event-driven dynamics (EventDrivenMap.cu:544-618) for exactly time_horizon;
+ *   restrict : linear interpolation of the fine state back onto the coarse knots, mean over realisations;
+ *   F(u)     : Phi_T(u) - u (the equationFree convention of Stability.cpp:68-71).
+ * Every entry point (compute_f, compute_f_batch, compute_dfdu, evolve/reduce_items_dev) then takes
+ * vectors of length n = 2 n_coarse; B200_EDM_DBG_POSITION holds the restricted profiles [ncols][R][n].
+ * n_coarse = 0 switches back to the reference's front map. */
+int b200_edm_set_profile_mode(b200_edm* h, uint32_t n_coarse);
+
 /* ---- sharded evaluation (one process per GPU) ----
  * Work item id = col * no_realisations + r.  evolve_items runs items [item_begin,
  * item_end) of the batch and writes, for local item k, M restricted front positions to
@@ -143,7 +157,7 @@ int b200_edm_last_counters(const b200_edm* h, uint64_t out[4]);
 /* SURVEY Q15 soft flag of the most recent call: 1 if some front started outside the
  * domain (EventDrivenMap.cu:365-372 leaves the index unassigned; here it is 0). */
 int b200_edm_last_init_clamped(const b200_edm* h, int* clamped);
-/* Launch tuning: neurons handled by one thread (0 = choose from no_neurons; 1,2,4,8,16).
+/* Launch tuning: neurons handled by one thread (0 = choose from no_neurons; 4, 8 or 16).
  * The reference fixes one neuron per thread (EventDrivenMap.cu:182,196). */
 int b200_edm_set_tuning(b200_edm* h, int neurons_per_thread);
 

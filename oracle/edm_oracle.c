@@ -77,6 +77,29 @@ int oracle_edm_compute_f(const oracle_edm_cfg* cfg, const double* z, double* f_o
                         : edm_compute_f_f64(cfg, z, f_out, aux, r_begin, r_end, nthreads);
 }
 
+int oracle_profile_compute_f(const oracle_edm_cfg* cfg, uint32_t n_coarse, const double* u, double* f_out,
+                             double* restricted_out, int32_t* accept_out, int32_t* event_count_out,
+                             uint32_t r_begin, uint32_t r_end, int nthreads) {
+  if (!cfg || !u || !f_out || cfg->N < 2 || cfg->R < 1) return -1;
+  return cfg->precision ? edm_profile_compute_f_f32(cfg, n_coarse, u, f_out, restricted_out, accept_out, event_count_out, r_begin, r_end, nthreads)
+                        : edm_profile_compute_f_f64(cfg, n_coarse, u, f_out, restricted_out, accept_out, event_count_out, r_begin, r_end, nthreads);
+}
+
+/* the analytic travelling-wave lift (LiftKernel) sampled on the fine grid: a physically sensible
+ * base state for the profile map */
+int oracle_edm_lift(const oracle_edm_cfg* cfg, const double* z, double* v_out, double* s_out) {
+  oracle_edm_aux aux;
+  memset(&aux, 0, sizeof(aux));
+  aux.lift_v = v_out; aux.lift_s = s_out;
+  oracle_edm_cfg c = *cfg;
+  c.R = 1;
+  double* f = (double*)malloc(sizeof(double) * c.M);
+  /* evolving one realisation is the price of reusing compute_f; cheap at test sizes */
+  int rc = oracle_edm_compute_f(&c, z, f, &aux, 0, 1, 1);
+  free(f);
+  return rc;
+}
+
 int oracle_edm_compute_dfdu(const oracle_edm_cfg* cfg, const double* u, double eps,
                             double* jac_out, double* f0_out, int nthreads) {
   const uint32_t n = cfg->M;

@@ -114,6 +114,14 @@ void oracle_edm_beta(const oracle_edm_cfg* cfg, double* beta_out);
  * form it: f0 = F(u); J(:,i) = (F(u + eps e_i) - f0) * pow(eps,-1).  jac n x n col-major. */
 int oracle_edm_compute_dfdu(const oracle_edm_cfg* cfg, const double* u, double eps,
                             double* jac_out, double* f0_out, int nthreads);
+/* Profile map Phi_T(u) - u on coarse profiles u = (V_c[n_coarse], S_c[n_coarse]) — NEW functionality
+ * (BASELINE config 5; not in the reference); definition at the head of the function in
+ * edm_oracle_impl.inc.  restricted_out [nr][2 n_coarse], accept_out [nr], event_count_out [nr] nullable. */
+int oracle_profile_compute_f(const oracle_edm_cfg* cfg, uint32_t n_coarse, const double* u, double* f_out,
+                             double* restricted_out, int32_t* accept_out, int32_t* event_count_out,
+                             uint32_t r_begin, uint32_t r_end, int nthreads);
+/* LiftKernel (EventDrivenMap.cu:505-542) on the fine grid: v_out[N], s_out[N] */
+int oracle_edm_lift(const oracle_edm_cfg* cfg, const double* z, double* v_out, double* s_out);
 /* the counter-based standard normal used for it (exposed for the RNG parity test) */
 double oracle_normal(uint64_t seed, uint64_t index);
 

@@ -180,3 +180,31 @@ def edm_beta(cfg):
 
 def normal(seed, index):
     return lib().oracle_normal(seed, index)
+
+
+def profile_compute_f(cfg, n_coarse, u, r_begin=0, r_end=0, nthreads=1):
+    """Profile map (config 5): returns (f, dict(restricted, accept, event_count))."""
+    u = np.ascontiguousarray(u, np.float64)
+    n = 2 * n_coarse
+    assert u.size == n
+    nr = (r_end - r_begin) if r_end > r_begin else cfg.R
+    f = np.empty(n); restricted = np.empty((nr, n)); accept = np.empty(nr, np.int32); evc = np.empty(nr, np.int32)
+    fn = lib().oracle_profile_compute_f
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_uint32, C.c_uint32, C.c_int]
+    rc = fn(C.addressof(cfg), n_coarse, _p(u), _p(f), _p(restricted), _p(accept), _p(evc), r_begin, r_end, nthreads)
+    if rc:
+        raise ValueError(f"oracle_profile_compute_f rc={rc}")
+    return f, dict(restricted=restricted, accept=accept, event_count=evc)
+
+
+def edm_lift(cfg, z):
+    v = np.empty(cfg.N); s = np.empty(cfg.N)
+    fn = lib().oracle_edm_lift
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = fn(C.addressof(cfg), _p(np.ascontiguousarray(z, np.float64)), _p(v), _p(s))
+    if rc:
+        raise ValueError(f"oracle_edm_lift rc={rc}")
+    return v, s

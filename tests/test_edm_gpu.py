@@ -70,7 +70,7 @@ def test_golden(b200, name):
     assert rel(m.DebugFetch("coupling")[::64], c["coupling_head"]) < RTOL
 
 
-@pytest.mark.parametrize("N,npt", [(1024, 0), (1024, 4), (1024, 16), (512, 2), (512, 8), (256, 1), (1000, 8), (96, 1), (2048, 8)])
+@pytest.mark.parametrize("N,npt", [(1024, 0), (1024, 4), (1024, 16), (512, 4), (512, 8), (256, 4), (1000, 8), (96, 4), (2048, 8), (4096, 16)])
 def test_vs_oracle_shapes_and_tunings(b200, oracle, N, npt):
     """Every launch shape (neurons per thread, ragged N) gives the oracle's event sequence."""
     R = 3

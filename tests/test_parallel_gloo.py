@@ -22,8 +22,15 @@ class OracleEngine:
         self.R, self.N, self.M, self.sigma, self.seed = R, N, M, sigma, seed
         self.evolved = []
 
-    def empty(self, rows):
-        return self.torch.zeros((rows, self.M + 1), dtype=self.torch.float64)
+    def empty(self, rows, cols=None):
+        return self.torch.zeros((rows, (self.M + 1) if cols is None else cols), dtype=self.torch.float64)
+
+    def columns(self, z_cols, out):
+        for c in range(z_cols.shape[1]):
+            cfg = self.O.edm_cfg(R=self.R, N=self.N, M=self.M, sigma=self.sigma, seed=self.seed)
+            f, _ = self.O.edm_compute_f(cfg, z_cols[:, c])
+            out[c] = self.torch.from_numpy(f)
+            self.evolved.append(("col", c))
 
     def evolve(self, z_cols, lo, hi, out):
         self.evolved.append([])
@@ -61,12 +68,51 @@ def _worker(rank, world, port, R, N, sigma, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     eng = OracleEngine(R, N, sigma=sigma)
-    sj = parallel.ShardedJacobian([13.0589], R, noNeurons=N, group=dist, engine=eng)
+    sj = parallel.ShardedJacobian([13.0589], R, noNeurons=N, group=dist, engine=eng, shard="items")
     J, f0 = sj.ComputeDFDU(Z_DRIVER, 1e-2, return_f0=True)
     f = sj.ComputeF(Z_DRIVER)
     q.put((rank, J, f0, f, eng.evolved))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _worker_columns(rank, world, port, R, N, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from armadillocudalinearinterpolation_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = OracleEngine(R, N)
+    sj = parallel.ShardedJacobian([13.0589], R, noNeurons=N, group=dist, engine=eng, shard="columns")
+    zc = np.stack([Z_DRIVER + [0.002 * i, 0, 0] for i in range(5)], axis=1)   # 5 columns over 2 ranks: ragged
+    f = sj.ComputeFBatch(zc)
+    q.put((rank, f, len(eng.evolved)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_column_sharding_world2(oracle):
+    """Many-column batches (the profile map's 1001-column Jacobian) shard by whole columns: each rank
+    reduces its own columns and only the residual columns are all-gathered."""
+    import torch.multiprocessing as mp
+    R, N, world = 2, 512, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_columns, args=(r, world, port, R, N, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0][1], res[1][1])
+    assert (res[0][2], res[1][2]) == (3, 2)          # ceil(5/2) columns on rank 0, the rest on rank 1
+    cfg = oracle.edm_cfg(R=R, N=N)
+    for c in range(5):
+        fo, _ = oracle.edm_compute_f(cfg, Z_DRIVER + [0.002 * c, 0, 0])
+        assert np.array_equal(res[0][1][:, c], fo)
 
 
 def _free_port():
