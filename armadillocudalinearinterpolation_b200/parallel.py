@@ -76,8 +76,8 @@ class GpuEngine:
     def columns(self, z_cols, out):
         """Whole columns on this rank: out[c, :] = F(z_cols[:, c]) (host-buffer batch call)."""
         if z_cols.shape[1]:
-            f = self.map.ComputeFBatch(z_cols)
-            out[:z_cols.shape[1]] = self.torch.from_numpy(np.ascontiguousarray(f.T)).to(self.device)
+            f = self.map.ComputeFBatch(z_cols)           # (n, ncols) column-major = [ncols][n] in memory
+            out[:z_cols.shape[1]].copy_(self.torch.from_numpy(f.T))
 
     def set_profile_mode(self, n_coarse):
         self.map.SetProfileMode(n_coarse)
@@ -104,24 +104,31 @@ class ShardedJacobian:
         self.engine.set_profile_mode(n_coarse)
         self.M = self.engine.M
 
-    def _columns(self, z_cols):
+    def _columns_t(self, z_cols):
+        """Column sharding; returns the gathered residuals as a [ncols][n] tensor (engine's device)."""
         ncols = z_cols.shape[1]
         per, slices = partition_items(ncols, self.world)
         lo, hi = slices[self.rank]
         n = z_cols.shape[0]
         local = self.engine.empty(per, n)
-        self.engine.columns(np.asfortranarray(z_cols[:, lo:hi]), local)
+        self.engine.columns(z_cols[:, lo:hi], local)
         if self.world > 1:
             gathered = self.engine.empty(per * self.world, n)
             self.dist.all_gather_into_tensor(gathered, local)
         else:
             gathered = local
-        return np.asfortranarray(gathered[:ncols].cpu().numpy().T)
+        return gathered[:ncols]
+
+    def _columns(self, z_cols):
+        return np.asfortranarray(self._columns_t(z_cols).cpu().numpy().T)
+
+    def _use_columns(self, ncols):
+        return self.shard == "columns" or (self.shard == "auto" and ncols >= 2 * self.world and self.world > 1)
 
     def ComputeFBatch(self, z_cols):
         z_cols = np.asfortranarray(z_cols, np.float64)
         ncols = z_cols.shape[1]
-        if self.shard == "columns" or (self.shard == "auto" and ncols >= 2 * self.world and self.world > 1):
+        if self._use_columns(ncols):
             return self._columns(z_cols)
         n_items = ncols * self.R
         per, slices = partition_items(n_items, self.world)
@@ -139,6 +146,15 @@ class ShardedJacobian:
         return self.ComputeFBatch(np.asarray(u, np.float64).reshape(-1, 1))[:, 0]
 
     def ComputeDFDU(self, u, eps, return_f0=False):
-        f_cols = self.ComputeFBatch(fd_columns(u, eps))
+        z = fd_columns(u, eps)
+        n = z.shape[0]
+        if self._use_columns(n + 1):
+            # difference on the engine's device (same two IEEE operations as NewtonSolver.cpp:194),
+            # one transfer of the finished Jacobian
+            g = self._columns_t(z)
+            Jt = (g[:n] - g[n]) * eps ** -1
+            J = np.asfortranarray(Jt.cpu().numpy().T)
+            return (J, g[n].cpu().numpy().copy()) if return_f0 else J
+        f_cols = self.ComputeFBatch(z)
         J, f0 = fd_jacobian_from_columns(f_cols, eps)
         return (J, f0) if return_f0 else J

@@ -397,7 +397,7 @@ def main():
         xf = -3.0 + 6.0 / 1024 * np.arange(1024); xc = -3.0 + 6.0 / nc * np.arange(nc)
         u0 = np.concatenate([np.interp(xc, xf, lv), np.interp(xc, xf, ls)])
         R5 = 1000 if args.config5_full else 64
-        pj = parallel.ShardedJacobian([BETA], R5, noNeurons=1024, group=dist, shard="columns" if world > 1 else "items")
+        pj = parallel.ShardedJacobian([BETA], R5, noNeurons=1024, group=dist, shard="columns")
         pj.engine.map.SetTimeHorizon(1.0)
         pj.SetProfileMode(nc)
         J5 = pj.ComputeDFDU(u0, 1e-3)
