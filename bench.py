@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--config5-full", action="store_true", help="profile-map stability at R = 1000 (1e6 neurons per column)")
+    ap.add_argument("--only-config5", action="store_true", help="of the secondary workloads run only the profile-map stability")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -307,85 +308,86 @@ def main():
     # ---------------- secondary workloads ----------------
     if not args.no_extra:
         extra = {}
-        # configs[0]: 1-D, 1e6 knots, 1e7 queries; 8 rotating query/output buffer pairs (1.28 GB)
-        # so that consecutive launches never find their streams in L2
-        rng = np.random.default_rng(1234)
-        ng, ni, nbuf = 1_000_000, 10_000_000, 8
-        for kind in ("uniform", "nonuniform"):
-            xg = np.linspace(0.0, 1.0, ng) if kind == "uniform" else np.cumsum(0.5 + rng.random(ng))
-            xg = (xg - xg[0]) / (xg[-1] - xg[0])
-            yg = np.sin(2 * np.pi * xg) + 0.1 * np.random.default_rng(1235).standard_normal(ng)
-            p1 = B.Interp1Plan(xg, yg)
-            for order in ("unsorted", "sorted"):
-                g1 = torch.Generator(device="cuda").manual_seed(1236)
-                qs = [torch.rand(ni, generator=g1, device="cuda", dtype=torch.float64) for _ in range(nbuf)]
-                if order == "sorted":
-                    qs = [q.sort().values for q in qs]
-                outs = [torch.empty_like(q) for q in qs]
-                state = {"i": 0}
+        if not args.only_config5:
+            # configs[0]: 1-D, 1e6 knots, 1e7 queries; 8 rotating query/output buffer pairs (1.28 GB)
+            # so that consecutive launches never find their streams in L2
+            rng = np.random.default_rng(1234)
+            ng, ni, nbuf = 1_000_000, 10_000_000, 8
+            for kind in ("uniform", "nonuniform"):
+                xg = np.linspace(0.0, 1.0, ng) if kind == "uniform" else np.cumsum(0.5 + rng.random(ng))
+                xg = (xg - xg[0]) / (xg[-1] - xg[0])
+                yg = np.sin(2 * np.pi * xg) + 0.1 * np.random.default_rng(1235).standard_normal(ng)
+                p1 = B.Interp1Plan(xg, yg)
+                for order in ("unsorted", "sorted"):
+                    g1 = torch.Generator(device="cuda").manual_seed(1236)
+                    qs = [torch.rand(ni, generator=g1, device="cuda", dtype=torch.float64) for _ in range(nbuf)]
+                    if order == "sorted":
+                        qs = [q.sort().values for q in qs]
+                    outs = [torch.empty_like(q) for q in qs]
+                    state = {"i": 0}
 
-                def step1():
-                    i = state["i"] % nbuf
-                    state["i"] += 1
-                    p1(qs[i], out=outs[i])
-                k1 = max(args.steps, 16)
-                ms1 = time_steps(torch, step1, k1, 3, dist) / k1
-                gbs = (16 * ni + 16 * ng) / (ms1 * 1e-3) / 1e9
-                extra[f"interp1_f64_1e6knots_1e7queries_{kind}_{order}"] = {
-                    "points_per_s": n_gpus * ni / (ms1 * 1e-3), "ms_per_launch": ms1, "lookup_mode": p1.lookup_mode,
-                    "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
-                del qs, outs
-            p1.close()
-        # configs[1] grid shape (Armadillo's own interp2 API): 1e4 x 1e4 sorted points
-        g2 = torch.Generator(device="cuda").manual_seed(2236)
-        xi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
-        yi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
-        msg = time_steps(torch, lambda: plan.grid(xi, yi), max(5, args.steps // 2), 3, dist) / max(5, args.steps // 2)
-        gb = (8 * 1e8 + ALG_BYTES_GRID + 16 * 1e4) / (msg * 1e-3) / 1e9
-        extra["interp2_grid_f64_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msg * 1e-3), "ms_per_launch": msg,
-                                             "algorithmic_GBps": gb, "roofline_frac": gb / peak}
-        # configs[1] with tile-sorted queries (SURVEY 8d variant iii): same points, ordered by grid cell
-        cell = (xq * (NX - 1)).floor().to(torch.int64) * NY + (yq * (NY - 1)).floor().to(torch.int64)
-        order = cell.argsort()
-        del cell
-        xs, ys = xq[order], yq[order]
-        del order
-        nst = max(5, args.steps // 2)
-        mss = time_steps(torch, lambda: plan.scattered(xs, ys, out=zq), nst, 3, dist) / nst
-        gbs = alg_bytes / (mss * 1e-3) / 1e9
-        extra["interp2_scattered_f64_cell_sorted_queries"] = {"points_per_s": n_gpus * NQ / (mss * 1e-3), "ms_per_launch": mss,
-                                                              "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
-        del xs, ys
-        # configs[2]: one map evaluation, parameters.hpp default ensemble (R=1000, N=1024, M=3, T=5)
-        for sigma in (0.0, 0.5):
-            m = B.EventDrivenMap([BETA], 1000, noNeurons=1024)
-            m.SetParameterStdDev(sigma); m.SetSeed(42); m.EnableTiming(True)
+                    def step1():
+                        i = state["i"] % nbuf
+                        state["i"] += 1
+                        p1(qs[i], out=outs[i])
+                    k1 = max(args.steps, 16)
+                    ms1 = time_steps(torch, step1, k1, 3, dist) / k1
+                    gbs = (16 * ni + 16 * ng) / (ms1 * 1e-3) / 1e9
+                    extra[f"interp1_f64_1e6knots_1e7queries_{kind}_{order}"] = {
+                        "points_per_s": n_gpus * ni / (ms1 * 1e-3), "ms_per_launch": ms1, "lookup_mode": p1.lookup_mode,
+                        "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+                    del qs, outs
+                p1.close()
+            # configs[1] grid shape (Armadillo's own interp2 API): 1e4 x 1e4 sorted points
+            g2 = torch.Generator(device="cuda").manual_seed(2236)
+            xi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
+            yi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
+            msg = time_steps(torch, lambda: plan.grid(xi, yi), max(5, args.steps // 2), 3, dist) / max(5, args.steps // 2)
+            gb = (8 * 1e8 + ALG_BYTES_GRID + 16 * 1e4) / (msg * 1e-3) / 1e9
+            extra["interp2_grid_f64_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msg * 1e-3), "ms_per_launch": msg,
+                                                 "algorithmic_GBps": gb, "roofline_frac": gb / peak}
+            # configs[1] with tile-sorted queries (SURVEY 8d variant iii): same points, ordered by grid cell
+            cell = (xq * (NX - 1)).floor().to(torch.int64) * NY + (yq * (NY - 1)).floor().to(torch.int64)
+            order = cell.argsort()
+            del cell
+            xs, ys = xq[order], yq[order]
+            del order
+            nst = max(5, args.steps // 2)
+            mss = time_steps(torch, lambda: plan.scattered(xs, ys, out=zq), nst, 3, dist) / nst
+            gbs = alg_bytes / (mss * 1e-3) / 1e9
+            extra["interp2_scattered_f64_cell_sorted_queries"] = {"points_per_s": n_gpus * NQ / (mss * 1e-3), "ms_per_launch": mss,
+                                                                  "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+            del xs, ys
+            # configs[2]: one map evaluation, parameters.hpp default ensemble (R=1000, N=1024, M=3, T=5)
+            for sigma in (0.0, 0.5):
+                m = B.EventDrivenMap([BETA], 1000, noNeurons=1024)
+                m.SetParameterStdDev(sigma); m.SetSeed(42); m.EnableTiming(True)
+                for _ in range(3):
+                    m.ComputeF(Z_DRIVER)
+                reps = 10
+                t0 = time.perf_counter()
+                evolve_ms = []
+                for _ in range(reps):
+                    m.ComputeF(Z_DRIVER)
+                    evolve_ms.append(m.LastEvolveMs())
+                call_ms = 1e3 * (time.perf_counter() - t0) / reps
+                cnt = m.LastCounters()
+                extra[f"map_eval_R1000_N1024_sigma{sigma}"] = {
+                    "evals_per_s_per_gpu": 1e3 / call_ms, "ms_per_compute_f": call_ms, "evolve_kernel_ms": float(np.mean(evolve_ms)),
+                    "events": cnt["events"], "neuron_event_updates_per_s": cnt["events"] * 1024 / (np.mean(evolve_ms) * 1e-3),
+                    "candidates": cnt["candidates"], "newton_its": cnt["newton_its"],
+                    "fp64_fma_peak_tflops_measured": fp64_peak}
+                m.close()
+            # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
+            # items sharded over the ranks, positions gathered with one NCCL all-gather
+            jm = parallel.ShardedJacobian([BETA], 1000, noNeurons=1024, group=dist)
             for _ in range(3):
-                m.ComputeF(Z_DRIVER)
+                jm.ComputeDFDU(Z_DRIVER, 1e-2)
             reps = 10
-            t0 = time.perf_counter()
-            evolve_ms = []
-            for _ in range(reps):
-                m.ComputeF(Z_DRIVER)
-                evolve_ms.append(m.LastEvolveMs())
-            call_ms = 1e3 * (time.perf_counter() - t0) / reps
-            cnt = m.LastCounters()
-            extra[f"map_eval_R1000_N1024_sigma{sigma}"] = {
-                "evals_per_s_per_gpu": 1e3 / call_ms, "ms_per_compute_f": call_ms, "evolve_kernel_ms": float(np.mean(evolve_ms)),
-                "events": cnt["events"], "neuron_event_updates_per_s": cnt["events"] * 1024 / (np.mean(evolve_ms) * 1e-3),
-                "candidates": cnt["candidates"], "newton_its": cnt["newton_its"],
-                "fp64_fma_peak_tflops_measured": fp64_peak}
-            m.close()
-        # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
-        # items sharded over the ranks, positions gathered with one NCCL all-gather
-        jm = parallel.ShardedJacobian([BETA], 1000, noNeurons=1024, group=dist)
-        for _ in range(3):
-            jm.ComputeDFDU(Z_DRIVER, 1e-2)
-        reps = 10
-        msj = wall_steps(torch, lambda: jm.ComputeDFDU(Z_DRIVER, 1e-2), reps, 0, dist) / reps
-        extra["fd_jacobian_n3_R1000_N1024"] = {"jacobians_per_s": 1e3 / msj, "map_evals_per_s": 4e3 / msj,
-                                               "ms_per_jacobian": msj, "ranks": n_gpus, "scaling": "strong",
-                                               "collective": "all_gather of (items x 3) positions" if world > 1 else "none"}
+            msj = wall_steps(torch, lambda: jm.ComputeDFDU(Z_DRIVER, 1e-2), reps, 0, dist) / reps
+            extra["fd_jacobian_n3_R1000_N1024"] = {"jacobians_per_s": 1e3 / msj, "map_evals_per_s": 4e3 / msj,
+                                                   "ms_per_jacobian": msj, "ranks": n_gpus, "scaling": "strong",
+                                                   "collective": "all_gather of (items x 3) positions" if world > 1 else "none"}
         # configs[4]: stability analysis on a 1e3-dim coarse PROFILE (profile map: n = 2 x 500 knots),
         # 1001 evaluations per Jacobian; columns sharded over the ranks, residual columns all-gathered.
         # R = 64 realisations per column by default (--config5-full: R = 1000, i.e. 1e6 neurons per column)
