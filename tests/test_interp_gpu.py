@@ -167,3 +167,35 @@ def test_full_size_properties_config2(b200):
     err = (zq - ref).abs().max().item()
     assert err < 5e-15
     assert not torch.isnan(zq).any().item()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_interp2_axes_too_large_for_shared_memory(b200, oracle, dt):
+    """Knot vectors beyond the shared-memory budget fall back to the global-table kernel: same bits."""
+    rng = np.random.default_rng(15)
+    nx, ny = (14500, 16) if dt == np.float64 else (29000, 16)
+    x = np.unique(np.cumsum(0.5 + rng.random(nx)).astype(dt)); y = np.linspace(0, 1, ny).astype(dt)
+    z = rng.standard_normal((y.size, x.size)).astype(dt)
+    plan = b200.Interp2Plan(x, y, z)
+    xq = rng.uniform(x[0], x[-1], 200_000).astype(dt); yq = rng.random(200_000).astype(dt)
+    assert same_bits(plan.scattered(xq, yq), oracle.interp2_scattered(x, y, z, xq, yq, nthreads=8))
+
+
+def test_interp2_layout_flags_give_identical_bits(b200, oracle):
+    """Column-major gathers and 2x2 corner records are two layouts of the same arithmetic."""
+    import ctypes as C
+    from armadillocudalinearinterpolation_b200 import _lib
+    rng = np.random.default_rng(16)
+    x = np.linspace(0, 1, 300); y = np.linspace(0, 1, 200); z = np.asfortranarray(rng.standard_normal((200, 300)))
+    xq = rng.uniform(-0.1, 1.1, 100_000); yq = rng.uniform(-0.1, 1.1, 100_000)
+    ref = oracle.interp2_scattered(x, y, z, xq, yq, extrap=1.5)
+    L = _lib.lib()
+    for flags in (1, 2):   # B200_INTERP2_NO_CELLS, B200_INTERP2_FORCE_CELLS
+        h = C.c_void_p()
+        _lib.check(L.b200_interp2_plan_create_ex(0, x.ctypes.data_as(C.c_void_p), C.c_size_t(x.size), y.ctypes.data_as(C.c_void_p),
+                                                 C.c_size_t(y.size), z.ctypes.data_as(C.c_void_p), C.c_uint(flags), C.byref(h)))
+        out = np.empty_like(xq)
+        _lib.check(L.b200_interp2_scattered(h, xq.ctypes.data_as(C.c_void_p), yq.ctypes.data_as(C.c_void_p), C.c_size_t(xq.size),
+                                            out.ctypes.data_as(C.c_void_p), C.c_double(1.5)))
+        L.b200_interp2_plan_destroy(h)
+        assert same_bits(out, ref)
