@@ -834,6 +834,9 @@ struct b200_edm {
   uint64_t seed = 42;
   int debug = 0, timing = 0, npt = 0;
   uint32_t profile_nc = 0;   // 0: front map; > 0: profile map on this many coarse knots
+  // in-process multi-GPU: helper handles on other devices of this process (b200_edm_set_devices)
+  std::vector<b200_edm*> helpers;
+  cudaEvent_t ev_helper = nullptr;
   void* d_uc = nullptr;      // profile map: columns converted to the run's arithmetic type
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -1113,6 +1116,50 @@ int upload_z(b200_edm* h, const double* z_cols, size_t n, size_t ncols, cudaStre
   return B200_OK;
 }
 
+// copy everything that defines the map from the primary handle to a helper on another device
+void sync_helper(const b200_edm* h, b200_edm* g) {
+  if (g->params != h->params || g->sigma != h->sigma || g->seed != h->seed || g->R != h->R || g->N != h->N) g->beta_dirty = true;
+  if (g->N != h->N || memcmp(&g->model, &h->model, sizeof(h->model)) != 0) g->w_dirty = true;
+  if (g->R != h->R || g->N != h->N || g->Mf != h->Mf || g->profile_nc != h->profile_nc) { cudaSetDevice(g->device); free_batch(g); }
+  g->params = h->params; g->model = h->model; g->R = h->R; g->N = h->N; g->Mf = h->Mf; g->prec = h->prec;
+  g->sigma = h->sigma; g->seed = h->seed; g->npt = h->npt; g->profile_nc = h->profile_nc;
+  g->debug = 0; g->timing = 0;
+}
+
+// In-process multi-GPU: the (column, realisation) items are split over the primary device and the
+// helpers; every device lifts all columns (cheap) and evolves its slice on its own stream; the
+// helpers' positions / accept flags are copied peer-to-peer into the primary's item-ordered arrays,
+// where the usual fixed-order reduction runs — bitwise the single-device result.
+template <typename T>
+int evolve_multi(b200_edm* h, const double* z_cols, size_t n, size_t ncols, cudaStream_t st) {
+  const size_t nitems = ncols * h->R, ndev = h->helpers.size() + 1, nd = ndim(h), es = esize(h);
+  const size_t per = (nitems + ndev - 1) / ndev;
+  // helpers first (they run while the primary works on its own slice)
+  for (size_t d = 1; d < ndev; ++d) {
+    b200_edm* g = h->helpers[d - 1];
+    const size_t lo = d * per < nitems ? d * per : nitems, hi = (d + 1) * per < nitems ? (d + 1) * per : nitems;
+    if (hi <= lo) continue;
+    sync_helper(h, g);
+    B200_CUDA(cudaSetDevice(g->device));
+    B200_TRY(ensure_batch(g, ncols, hi - lo));
+    B200_TRY(ensure_ensemble<T>(g, g->stream));
+    B200_TRY(upload_z(g, z_cols, n, ncols, g->stream));
+    B200_TRY(run_prepare<T>(g, ncols, g->stream));
+    B200_TRY(run_evolve<T>(g, lo, hi, (T*)g->d_pos, g->d_accept, g->stream));
+    B200_CUDA(cudaMemcpyPeerAsync((char*)h->d_pos + lo * nd * es, h->device, g->d_pos, g->device, (hi - lo) * nd * es, g->stream));
+    B200_CUDA(cudaMemcpyPeerAsync(h->d_accept + lo, h->device, g->d_accept, g->device, (hi - lo) * sizeof(int32_t), g->stream));
+    B200_CUDA(cudaEventRecord(g->ev_done, g->stream));
+  }
+  B200_CUDA(cudaSetDevice(h->device));
+  const size_t hi0 = per < nitems ? per : nitems;
+  B200_TRY(run_evolve<T>(h, 0, hi0, (T*)h->d_pos, h->d_accept, st));
+  for (size_t d = 1; d < ndev; ++d) {
+    const size_t lo = d * per < nitems ? d * per : nitems, hi = (d + 1) * per < nitems ? (d + 1) * per : nitems;
+    if (hi > lo) B200_CUDA(cudaStreamWaitEvent(st, h->helpers[d - 1]->ev_done, 0));
+  }
+  return B200_OK;
+}
+
 template <typename T>
 int compute_batch(b200_edm* h, const double* z_cols, size_t n, size_t ncols, double* f_out) {
   B200_CUDA(cudaSetDevice(h->device));
@@ -1123,7 +1170,8 @@ int compute_batch(b200_edm* h, const double* z_cols, size_t n, size_t ncols, dou
   B200_TRY(ensure_ensemble<T>(h, st));
   B200_TRY(upload_z(h, z_cols, n, ncols, st));
   B200_TRY(run_prepare<T>(h, ncols, st));
-  B200_TRY(run_evolve<T>(h, 0, nitems, (T*)h->d_pos, h->d_accept, st));
+  if (!h->helpers.empty()) B200_TRY(evolve_multi<T>(h, z_cols, n, ncols, st));
+  else B200_TRY(run_evolve<T>(h, 0, nitems, (T*)h->d_pos, h->d_accept, st));
   B200_TRY(run_reduce<T>(h, ncols, (const T*)h->d_pos, h->d_accept, h->d_f, st));
   double* h_f = h->h_pin + n * ncols;
   B200_CUDA(cudaMemcpyAsync(h_f, h->d_f, n * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1180,6 +1228,8 @@ int b200_edm_create(const double* params, size_t nparams, uint32_t no_realisatio
 
 int b200_edm_destroy(b200_edm* h) {
   if (!h) return B200_OK;
+  for (b200_edm* g : h->helpers) b200_edm_destroy(g);
+  h->helpers.clear();
   cudaSetDevice(h->device);
   free_ensemble(h);
   free_batch(h);
@@ -1261,6 +1311,37 @@ int b200_edm_new_seed(b200_edm* h) {
   h->beta_dirty = true;
   return B200_OK;
 }
+int b200_edm_set_devices(b200_edm* h, const int* device_ids, size_t ndevices) {
+  B200_TRY(check_handle(h, "edm_set_devices"));
+  if (!device_ids || ndevices < 1) return fail(B200_ERR_INVALID_ARG, "edm_set_devices: empty device list");
+  if (device_ids[0] != h->device) return fail(B200_ERR_INVALID_ARG, "edm_set_devices: the first device must be the handle's own (%d)", h->device);
+  int count = 0;
+  B200_CUDA(cudaGetDeviceCount(&count));
+  for (size_t i = 0; i < ndevices; ++i) {
+    if (device_ids[i] < 0 || device_ids[i] >= count) return fail(B200_ERR_INVALID_ARG, "edm_set_devices: device %d does not exist", device_ids[i]);
+    for (size_t j = 0; j < i; ++j) if (device_ids[j] == device_ids[i]) return fail(B200_ERR_INVALID_ARG, "edm_set_devices: device %d listed twice", device_ids[i]);
+  }
+  for (b200_edm* g : h->helpers) b200_edm_destroy(g);
+  h->helpers.clear();
+  int rc = B200_OK;
+  for (size_t i = 1; i < ndevices && rc == B200_OK; ++i) {
+    rc = cudaSetDevice(device_ids[i]) == cudaSuccess ? B200_OK : fail(B200_ERR_CUDA, "cudaSetDevice(%d) failed", device_ids[i]);
+    b200_edm* g = nullptr;
+    if (rc == B200_OK) rc = b200_edm_create(h->params.data(), h->params.size(), h->R, h->N, h->Mf, h->prec, &g);
+    if (rc == B200_OK) {
+      h->helpers.push_back(g);
+      // direct NVLink copies where the topology allows; staged through the host otherwise
+      cudaDeviceEnablePeerAccess(h->device, 0);
+      cudaSetDevice(h->device);
+      cudaDeviceEnablePeerAccess(device_ids[i], 0);
+      cudaGetLastError();
+    }
+  }
+  cudaSetDevice(h->device);
+  if (rc != B200_OK) { for (b200_edm* g : h->helpers) b200_edm_destroy(g); h->helpers.clear(); }
+  return rc;
+}
+
 int b200_edm_set_profile_mode(b200_edm* h, uint32_t n_coarse) {
   B200_TRY(check_handle(h, "edm_set_profile_mode"));
   if (n_coarse == 1) return fail(B200_ERR_INVALID_ARG, "profile map needs at least 2 coarse knots (0 switches it off)");

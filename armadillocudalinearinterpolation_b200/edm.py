@@ -146,6 +146,11 @@ class EventDrivenMap:
         self.M = 2 * int(n_coarse) if n_coarse else self._fronts
         self._last_cols = 0
 
+    def SetDevices(self, device_ids):
+        """Split every evaluation over these devices of this process (first = the handle's own device)."""
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        check(self._L.b200_edm_set_devices(self._h, ids, C.c_size_t(len(device_ids))))
+
     def SetTuning(self, neurons_per_thread):
         check(self._L.b200_edm_set_tuning(self._h, int(neurons_per_thread)))
 

@@ -70,6 +70,9 @@ void EventDrivenMapB200::SetSeed(unsigned long long seed) { Check(b200_edm_set_s
 void EventDrivenMapB200::SetProfileMode(unsigned int nCoarse) {
   Check(b200_edm_set_profile_mode(mpHandle, nCoarse), "SetProfileMode");
 }
+void EventDrivenMapB200::SetDevices(const int* deviceIds, unsigned int nDevices) {
+  Check(b200_edm_set_devices(mpHandle, deviceIds, nDevices), "SetDevices");
+}
 void EventDrivenMapB200::SetDebugFlag(const bool val) {
   Check(b200_edm_set_debug(mpHandle, val ? 1 : 0), "SetDebugFlag");
   if (mPrint) std::cout << (val ? "Debugging on" : "Debugging off") << std::endl;

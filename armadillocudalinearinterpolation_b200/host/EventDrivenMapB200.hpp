@@ -46,6 +46,8 @@ class EventDrivenMapB200 : public AbstractNonlinearProblem, public AbstractNonli
   void SetSeed(unsigned long long seed);
   // profile map (BASELINE config 5, see b200_edm_set_profile_mode): vectors become (V_c, S_c), n = 2 nCoarse
   void SetProfileMode(unsigned int nCoarse);
+  // split every evaluation over several GPUs of this process (first id = the device the map was created on)
+  void SetDevices(const int* deviceIds, unsigned int nDevices);
   void SetPrintOutput(bool on) { mPrint = on; }
   // n x ncols evaluation points -> n x ncols residuals, one launch
   void ComputeFBatch(const arma::mat& uCols, arma::mat& fCols);

@@ -2,7 +2,7 @@
 // the beta-continuation loop that the reference leaves commented out (Driver.cu:86-112):
 // solve for the travelling wave, count unstable eigenvalues, step beta, reuse the solution.
 //
-//   driver_b200 [steps=3] [noReal=1000] [noNeurons=1024] [dbeta=0.1]
+//   driver_b200 [steps=3] [noReal=1000] [noNeurons=1024] [dbeta=0.1] [nGpus=1]
 #include <armadillo>
 #include <chrono>
 #include <cstdlib>
@@ -17,12 +17,18 @@ int main(int argc, char* argv[]) {
   const unsigned noReal = argc > 2 ? (unsigned)std::atoi(argv[2]) : 1000;
   const unsigned noNeurons = argc > 3 ? (unsigned)std::atoi(argv[3]) : 1024;
   const double dbeta = argc > 4 ? std::atof(argv[4]) : 0.1;
+  const int nGpus = argc > 5 ? std::atoi(argv[5]) : 1;
 
   arma::vec parameters(1);
   parameters << 13.0589f;                                  // Driver.cu:16
   EventDrivenMap map(&parameters, noReal);                 // Driver.cu:20
   if (noNeurons != 1024) map.SetNoThreads((int)noNeurons);
   map.SetFiniteDifferenceEpsilon(1e-2);                    // Driver.cu:37
+  if (nGpus > 1) {                                         // every evaluation split over the GPUs of this process
+    int ids[16];
+    for (int i = 0; i < nGpus && i < 16; ++i) ids[i] = i;
+    map.SetDevices(ids, (unsigned)(nGpus < 16 ? nGpus : 16));
+  }
 
   arma::vec guess(noSpikes);
   guess << 0.3310f << 0.6914f << 1.3557f;                  // Driver.cu:24

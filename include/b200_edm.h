@@ -108,6 +108,12 @@ int b200_edm_compute_dfdu(b200_edm* h, const double* u, size_t n, double eps,
  * n_coarse = 0 switches back to the reference's front map. */
 int b200_edm_set_profile_mode(b200_edm* h, uint32_t n_coarse);
 
+/* ---- in-process multi-GPU (for C++ callers without a launcher) ----
+ * After this call compute_f / compute_f_batch / compute_dfdu split their (column, realisation) work
+ * items over the listed devices of THIS process (device_ids[0] must be the handle's device); results
+ * are bitwise those of a single device.  The reference is single-GPU (EventDrivenMap.cu:182,196). */
+int b200_edm_set_devices(b200_edm* h, const int* device_ids, size_t ndevices);
+
 /* ---- sharded evaluation (one process per GPU) ----
  * Work item id = col * no_realisations + r.  evolve_items runs items [item_begin,
  * item_end) of the batch and writes, for local item k, M restricted front positions to

@@ -196,3 +196,26 @@ def test_default_ensemble_full_size(b200, oracle):
     assert np.all(pos == pos[0])
     assert rel(pos[0], a["position"][0]) < RTOL
     assert np.max(np.abs(f - fo)) < RTOL * 2
+
+
+def test_in_process_multi_device_is_bitwise_single_device(b200):
+    """b200_edm_set_devices: items split over the GPUs of one process, reduced on the first —
+    same bits as one GPU (front map, heterogeneous ensemble, Jacobian, profile map)."""
+    n_dev = b200.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs in this process")
+    devs = list(range(min(n_dev, 4)))
+    zc = np.stack([Z_DRIVER, Z_DRIVER + [1e-2, 0, 0], Z_DRIVER + [0, 0, 1e-2]], axis=1)
+    for sigma in (0.0, 0.4):
+        a = make_map(b200, dict(R=37, N=512, sigma=sigma, seed=5))
+        b = make_map(b200, dict(R=37, N=512, sigma=sigma, seed=5))
+        b.SetDevices(devs)
+        assert np.array_equal(a.ComputeFBatch(zc), b.ComputeFBatch(zc))
+        assert np.array_equal(a.ComputeDFDU(Z_DRIVER, 1e-2), b.ComputeDFDU(Z_DRIVER, 1e-2))
+        b.SetNoThreads(1024); a.SetNoThreads(1024)          # helpers follow reconfiguration
+        assert np.array_equal(a.ComputeF(Z_DRIVER), b.ComputeF(Z_DRIVER))
+    a = make_map(b200, dict(R=5, N=512)); b = make_map(b200, dict(R=5, N=512)); b.SetDevices(devs)
+    for m in (a, b):
+        m.SetTimeHorizon(0.5); m.SetProfileMode(64)
+    u = np.concatenate([np.linspace(0.2, 0.95, 64), np.linspace(0.0, 0.5, 64)])
+    assert np.array_equal(a.ComputeF(u), b.ComputeF(u))
