@@ -53,7 +53,7 @@ for r in rows[1:]:
     a[0] += 1; a[1] += v
 tot = sum(a[1] for a in agg.values())
 L = [f"# Launch list of `python bench.py --steps 2 --warmup 3 --no-cpu` ({tag})", "",
-     "`ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv`; per-launch times are cold-cache and",
+     "`ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv`; per-launch times are cold-cache and",
      "serialised — compare SHARES.  torch kernels (random number generation, sort of the query batches, copies) set",
      "up the synthetic inputs outside the timed regions.", "", "| launches | total ms | share | block | grid (last) | kernel |", "|---|---|---|---|---|---|"]
 for k, (n, t, b, g) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
