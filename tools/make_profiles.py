@@ -1,6 +1,6 @@
 """Turn ncu exports in gpurun_out/ into the committed summaries under profiles/.
 
-    python scratch/make_profiles.py <raw.csv from `ncu --page raw --csv`> <launches.csv> <tag>
+    python tools/make_profiles.py <raw.csv from `ncu --page raw --csv`> <launches.csv> <tag>
 """
 import collections, csv, json, sys
 raw, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
