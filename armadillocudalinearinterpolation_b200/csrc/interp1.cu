@@ -20,6 +20,7 @@
 //             binary search only inside pathological buckets;
 //  * the blend is (1-w)*Y[a] + w*Y[b] with w = |X[a]-q| / (|X[a]-q| + |X[b]-q|), every
 //    operation individually rounded (__dmul_rn, ...), bit-identical to the CPU oracle.
+#include <cstdlib>
 #include "interp_common.cuh"
 
 namespace b200 {
@@ -86,6 +87,66 @@ interp1_scalar_kernel(AxisDev<T> ax, const T* __restrict__ seg, const T* __restr
   }
 }
 
+// ---- small grids: the whole grid staged in shared memory ----
+// The "coarse profile -> fine ensemble" case (a few thousand knots, millions of queries): persistent
+// CTAs copy the knots, the values and (for non-uniform knots) the bucket table into shared memory
+// once with TMA bulk copies and then stream queries; the bracket lookup and the two value reads never
+// leave the SM, so HBM carries exactly 16 bytes (f64) per query.
+constexpr int kSmem1Threads = 512;
+
+template <typename T, bool WANT_IDX>
+__global__ void __launch_bounds__(kSmem1Threads)
+interp1_smem_kernel(AxisDev<T> ax, const T* __restrict__ yg, const T* __restrict__ xi, T* __restrict__ yi,
+                    int32_t* __restrict__ idx, size_t nvec, T extrap) {
+  extern __shared__ __align__(128) unsigned char smem1[];
+  constexpr int V = Vec256<T>::n;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem1);
+  auto pad16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  const size_t xb_bytes = pad16(sizeof(T) * ax.n);
+  const size_t fb_bytes = ax.mode ? pad16(sizeof(int32_t) * ((size_t)ax.nb + 1)) : 0;
+  T* sx = reinterpret_cast<T*>(smem1 + 16);
+  T* sy = reinterpret_cast<T*>(smem1 + 16 + xb_bytes);
+  int32_t* sf = reinterpret_cast<int32_t*>(smem1 + 16 + 2 * xb_bytes);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (unsigned)(2 * xb_bytes + fb_bytes));
+    const unsigned chunk = 16384;
+    auto copy = [&](void* dst, const void* src, size_t bytes) {
+      for (size_t o = 0; o < bytes; o += chunk)
+        tma_bulk_g2s((unsigned char*)dst + o, (const unsigned char*)src + o, (unsigned)(bytes - o < chunk ? bytes - o : chunk), bar);
+    };
+    copy(sx, ax.x, xb_bytes);
+    copy(sy, yg, xb_bytes);
+    if (fb_bytes) copy(sf, ax.first, fb_bytes);
+  }
+  mbar_wait(bar, 0);
+  const AxisSmem<T> A = {sx, sf, ax.x0, ax.xmax, ax.inv_w, ax.n, ax.nb, ax.mode};
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    T q[V], y[V];
+    int32_t id[V];
+    ld_stream_256(xi + i * V, q);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const T qq = q[j];
+      if ((qq < A.x0) || (qq > A.xmax)) { id[j] = -1; y[j] = extrap; }
+      else if (qq != qq) { id[j] = -1; y[j] = qnan<T>(); }
+      else {
+        T xa, xb;
+        const int a = find_bracket_s(A, qq, xa, xb);
+        id[j] = a;
+        y[j] = blend(weight_of(xa, xb, qq), sy[a], sy[min(a + 1, A.n - 1)]);
+      }
+    }
+    st_stream_256(yi + i * V, y);
+    if (WANT_IDX) {
+      if (V == 8) st_stream_256(idx + i * V, reinterpret_cast<const int32_t(&)[8]>(id));
+      else st_stream_128(idx + i * V, reinterpret_cast<const int32_t(&)[4]>(id));
+    }
+  }
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -100,6 +161,7 @@ struct b200_interp1_plan {
   Axis<float> ax32;
   void* yg = nullptr;   // device copy of the values
   void* seg = nullptr;  // [ng][4] segment records
+  size_t smem_bytes = 0;  // > 0: the grid fits the shared-memory path
   cudaStream_t stream[2] = {nullptr, nullptr};
   // staging for host-buffer execution (allocated on first use)
   void* st_in[2] = {nullptr, nullptr};
@@ -131,11 +193,19 @@ int plan1_create(b200_interp1_plan* p, const T* xg, const T* yg, size_t ng) {
   B200_CUDA(cudaEventCreateWithFlags(&p->ev[0], cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&p->ev[1], cudaEventDisableTiming));
   B200_TRY(axis_create<T>(axis_of<T>(p), xg, ng, p->stream[0], "interp1 grid", true));
-  B200_CUDA(cudaMalloc(&p->yg, ng * sizeof(T)));
+  B200_CUDA(cudaMalloc(&p->yg, ng * sizeof(T) + 16));  // +16: bulk copies move whole 16-byte units
+  B200_CUDA(cudaMemsetAsync(p->yg, 0, ng * sizeof(T) + 16, p->stream[0]));
   B200_CUDA(cudaMalloc(&p->seg, ng * 4 * sizeof(T)));
   B200_CUDA(cudaMemcpyAsync(p->yg, yg, ng * sizeof(T), cudaMemcpyHostToDevice, p->stream[0]));
   B200_TRY(plan1_build_seg<T>(p, p->stream[0]));
   B200_CUDA(cudaStreamSynchronize(p->stream[0]));
+  {
+    auto pad16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const AxisDev<T>& ax = axis_of<T>(p).dev;
+    const size_t need = 16 + 2 * pad16(sizeof(T) * ng) + (ax.mode ? pad16(sizeof(int32_t) * ((size_t)ax.nb + 1)) : 0);
+    const char* e = getenv("B200_INTERP1_SMEM");
+    p->smem_bytes = (need <= 100 * 1024 && !(e && e[0] == '0')) ? need : 0;   // two CTAs per SM
+  }
   return B200_OK;
 }
 
@@ -150,7 +220,21 @@ int plan1_launch(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* i
   const bool aligned = (((uintptr_t)xi | (uintptr_t)yi) % 32 == 0) &&
                        (!idx || ((uintptr_t)idx % (V == 8 ? 32 : 16) == 0));
   size_t nvec = aligned ? ni / V : 0;
-  if (nvec) {
+  if (nvec && p->smem_bytes && nvec >= 4096) {
+    auto launch = [&](auto kern) -> int {
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+      int per_sm = 1, sms = 148;
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSmem1Threads, p->smem_bytes));
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+      const size_t blocks = (nvec + kSmem1Threads - 1) / kSmem1Threads;
+      const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+      kern<<<(int)(blocks < resident ? blocks : resident), kSmem1Threads, p->smem_bytes, st>>>(
+          ax, (const T*)p->yg, xi, yi, idx, nvec, extrap);
+      return B200_OK;
+    };
+    if (idx) B200_TRY(launch(interp1_smem_kernel<T, true>));
+    else B200_TRY(launch(interp1_smem_kernel<T, false>));
+  } else if (nvec) {
     // enough CTAs to fill 148 SMs x 8 resident CTAs; grid-stride beyond that
     size_t blocks = (nvec + kThreads - 1) / kThreads;
     int grid = (int)(blocks < (size_t)148 * 64 ? blocks : (size_t)148 * 64);
@@ -266,6 +350,7 @@ int b200_interp1_plan_destroy(b200_interp1_plan* p) {
 
 int b200_interp1_plan_lookup_mode(const b200_interp1_plan* p) {
   if (!p) return fail(B200_ERR_INVALID_ARG, "NULL plan");
+  if (p->smem_bytes) return 2;
   return p->dtype == B200_F64 ? p->ax64.dev.mode : p->ax32.dev.mode;
 }
 

@@ -338,6 +338,18 @@ def main():
                         "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
                     del qs, outs
                 p1.close()
+            # coarse profile -> fine ensemble: 1e3 knots staged in shared memory, 1e8 queries (1.6 GB of streams)
+            xg = np.linspace(-3.0, 3.0, 1000); yg = np.sin(xg)
+            p1 = B.Interp1Plan(xg, yg)
+            gs = torch.Generator(device="cuda").manual_seed(77)
+            qsm = torch.rand(NQ, generator=gs, device="cuda", dtype=torch.float64) * 6.0 - 3.0
+            osm = torch.empty_like(qsm)
+            nsm = max(5, args.steps // 2)
+            mssm = time_steps(torch, lambda: p1(qsm, out=osm), nsm, 3, dist) / nsm
+            gbs = (16 * NQ + 16 * 1000) / (mssm * 1e-3) / 1e9
+            extra["interp1_f64_1e3knots_1e8queries_smem"] = {"points_per_s": n_gpus * NQ / (mssm * 1e-3), "ms_per_launch": mssm,
+                                                             "lookup_mode": p1.lookup_mode, "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+            p1.close(); del qsm, osm
             # configs[1] grid shape (Armadillo's own interp2 API): 1e4 x 1e4 sorted points
             g2 = torch.Generator(device="cuda").manual_seed(2236)
             xi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values

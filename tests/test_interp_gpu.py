@@ -199,3 +199,30 @@ def test_interp2_layout_flags_give_identical_bits(b200, oracle):
                                             out.ctypes.data_as(C.c_void_p), C.c_double(1.5)))
         L.b200_interp2_plan_destroy(h)
         assert same_bits(out, ref)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["linspace", "cumsum", "clustered"])
+def test_interp1_small_grid_shared_memory_path(b200, oracle, dt, kind):
+    """Coarse profile -> fine ensemble: grids of a few thousand knots are staged in shared memory
+    (lookup mode 2); same bits and brackets as the oracle."""
+    rng = np.random.default_rng(17)
+    ng = 4001
+    if kind == "linspace":
+        xg = np.linspace(-3.0, 3.0, ng)
+    elif kind == "cumsum":
+        xg = np.cumsum(0.5 + rng.random(ng))
+    else:
+        xg = np.concatenate([np.linspace(0, 1e-3, ng - 50), np.linspace(0.1, 1.0, 50)])
+    xg = np.unique(xg.astype(dt))
+    yg = rng.standard_normal(xg.size).astype(dt)
+    xi = rng.uniform(xg[0] - 0.1, xg[-1] + 0.1, 1_000_001).astype(dt)
+    xi[:4] = [xg[0], xg[-1], np.nan, xg[17]]
+    plan = b200.Interp1Plan(xg, yg)
+    assert plan.lookup_mode == 2
+    yi, idx = plan(xi, extrap=0.25, return_index=True)
+    yo, io = oracle.interp1(xg, yg, xi, extrap=0.25, nthreads=8)
+    assert same_bits(yi, yo) and np.array_equal(idx, io)
+    yg2 = rng.standard_normal(xg.size).astype(dt)
+    plan.set_values(yg2)                                    # a new coarse profile on the same knots
+    assert same_bits(plan(xi, extrap=0.25), oracle.interp1(xg, yg2, xi, extrap=0.25, want_idx=False, nthreads=8))
