@@ -34,8 +34,10 @@ template <> struct Loader1<float> { using type = LoadSeg1F; };
 template <typename T>
 __device__ __forceinline__ T interp1_one(const AxisDev<T>& ax, const typename Loader1<T>::type& ld,
                                          T q, T extrap, int32_t& idx) {
-  if ((q < ax.x0) || (q > ax.xmax)) { idx = -1; return extrap; }
-  if (q != q) { idx = -1; return qnan<T>(); }
+  if (!(q >= ax.x0 && q <= ax.xmax)) {  // out of range -> extrap_val; NaN query -> NaN
+    idx = -1;
+    return (q != q) ? qnan<T>() : extrap;
+  }
   Seg1<T> sg;
   idx = find_bracket(ax, ld, q, sg);
   return blend(weight_of(sg.xa, sg.xb, q), sg.ya, sg.yb);
@@ -130,8 +132,7 @@ interp1_smem_kernel(AxisDev<T> ax, const T* __restrict__ yg, const T* __restrict
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const T qq = q[j];
-      if ((qq < A.x0) || (qq > A.xmax)) { id[j] = -1; y[j] = extrap; }
-      else if (qq != qq) { id[j] = -1; y[j] = qnan<T>(); }
+      if (!(qq >= A.x0 && qq <= A.xmax)) { id[j] = -1; y[j] = (qq != qq) ? qnan<T>() : extrap; }
       else {
         T xa, xb;
         const int a = find_bracket_s(A, qq, xa, xb);
