@@ -123,7 +123,7 @@ interp1_smem_kernel(AxisDev<T> ax, const T* __restrict__ yg, const T* __restrict
     if (fb_bytes) copy(sf, ax.first, fb_bytes);
   }
   mbar_wait(bar, 0);
-  const AxisSmem<T> A = {sx, sf, ax.x0, ax.xmax, ax.inv_w, ax.n, ax.nb, ax.mode};
+  const AxisSmem<T> A = {sx, sf, ax.x0, ax.xmax, ax.inv_w, ax.n, ax.nb, ax.mode, 0, (T)0};
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     T q[V], y[V];

@@ -100,7 +100,9 @@ class Interp2Plan:
     """Grid (X, Y, Z) resident in HBM.  Z is Y.size x X.size (rows follow Y), any memory order;
     it is stored column-major like arma::mat."""
 
-    def __init__(self, X, Y, Z):
+    NO_CELLS, FORCE_CELLS, NO_BANDS, FORCE_BANDS = 1, 2, 4, 8   # include/b200_interp.h layout flags
+
+    def __init__(self, X, Y, Z, flags=0):
         X = _np(X)
         Y = _np(Y, X.dtype)
         Z = np.asarray(Z)
@@ -110,8 +112,8 @@ class Interp2Plan:
         self.dtype = X.dtype
         self.nx, self.ny = X.size, Y.size
         self._h = C.c_void_p()
-        check(_lib.lib().b200_interp2_plan_create(_DT[X.dtype], _ptr(X), C.c_size_t(X.size), _ptr(Y),
-                                                 C.c_size_t(Y.size), _ptr(Zf), C.byref(self._h)))
+        check(_lib.lib().b200_interp2_plan_create_ex(_DT[X.dtype], _ptr(X), C.c_size_t(X.size), _ptr(Y),
+                                                    C.c_size_t(Y.size), _ptr(Zf), C.c_uint(flags), C.byref(self._h)))
 
     def grid(self, XI, YI, extrap=np.nan):
         """Tensor-grid queries (Armadillo's interp2 shape): returns ZI of shape (YI.size, XI.size)."""

@@ -226,3 +226,44 @@ def test_interp1_small_grid_shared_memory_path(b200, oracle, dt, kind):
     yg2 = rng.standard_normal(xg.size).astype(dt)
     plan.set_values(yg2)                                    # a new coarse profile on the same knots
     assert same_bits(plan(xi, extrap=0.25), oracle.interp1(xg, yg2, xi, extrap=0.25, want_idx=False, nthreads=8))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(513, 384, 300_001), (64, 50, 2047), (64, 50, 4097), (300, 200, 5), (1000, 37, 1_000_003)])
+def test_interp2_banded_pipeline_same_bits(b200, oracle, dt, shape):
+    """The L2-banded scattered pipeline (partition by column band -> interpolate band by band ->
+    un-permute; B200_INTERP2_FORCE_BANDS) is a re-ordering of the same arithmetic: same bits as the
+    oracle, including NaN / out-of-range queries in either coordinate, ragged tails and infinite extrap."""
+    import torch
+    nx, ny, nq = shape
+    rng = np.random.default_rng(18)
+    x = np.unique(np.cumsum(0.5 + rng.random(nx)).astype(dt)); y = np.linspace(-2, 3, ny).astype(dt)
+    z = rng.standard_normal((y.size, x.size)).astype(dt)
+    plan = b200.Interp2Plan(x, y, z, flags=b200.Interp2Plan.FORCE_CELLS | b200.Interp2Plan.FORCE_BANDS)
+    xq = rng.uniform(x[0] - 1, x[-1] + 1, nq).astype(dt); yq = rng.uniform(-2.1, 3.1, nq).astype(dt)
+    xq[:5] = [x[0], x[-1], np.nan, x[3], x[-1]]; yq[:5] = [y[0], y[-1], 0.0, np.nan, y[0]]
+    for extrap in (np.nan, 2.25, np.inf):
+        zq = plan.scattered(torch.from_numpy(xq).cuda(), torch.from_numpy(yq).cuda(), extrap=extrap)
+        torch.cuda.synchronize()
+        assert same_bits(zq.cpu().numpy(), oracle.interp2_scattered(x, y, z, xq, yq, extrap=extrap, nthreads=8))
+    # unaligned device buffers take the scalar load/store path of the same kernels
+    tx = torch.from_numpy(xq).cuda()[1:]; ty = torch.from_numpy(yq).cuda()[1:]
+    out = torch.empty(nq, dtype=tx.dtype, device="cuda")[1:]
+    plan.scattered(tx, ty, extrap=0.5, out=out)
+    torch.cuda.synchronize()
+    assert same_bits(out.cpu().numpy(), oracle.interp2_scattered(x, y, z, xq[1:], yq[1:], extrap=0.5, nthreads=8))
+
+
+def test_interp2_affine_axes_same_bits(b200, oracle, monkeypatch):
+    """linspace-style knots (x0 + j*step with two roundings, verified knot by knot at plan time) are
+    recomputed in the kernel instead of loaded; B200_INTERP_AFFINE=0 keeps the tables.  Same bits."""
+    rng = np.random.default_rng(19)
+    x = np.linspace(-1.0, 2.0, 1500); y = np.linspace(0.0, 1.0, 700)
+    z = rng.standard_normal((y.size, x.size))
+    xq = rng.uniform(-1.1, 2.1, 400_003); yq = rng.uniform(-0.1, 1.1, 400_003)
+    xq[:6] = [x[0], x[-1], np.nan, x[3], x[-2], np.nextafter(x[-1], 5.0)]; yq[:6] = [y[0], y[-1], 0.0, np.nan, y[-1], 0.5]
+    ref = oracle.interp2_scattered(x, y, z, xq, yq, extrap=-4.0, nthreads=8)
+    for affine in ("1", "0"):
+        monkeypatch.setenv("B200_INTERP_AFFINE", affine)
+        for flags in (0, b200.Interp2Plan.FORCE_CELLS, b200.Interp2Plan.NO_CELLS):
+            assert same_bits(b200.Interp2Plan(x, y, z, flags=flags).scattered(xq, yq, extrap=-4.0), ref)
