@@ -112,7 +112,7 @@ def test_interp2_vs_oracle(b200, oracle, dt):
     for extrap in (np.nan, 2.25):
         assert same_bits(plan.scattered(xq, yq, extrap=extrap), oracle.interp2_scattered(x, y, z, xq, yq, extrap=extrap, nthreads=8))
     xi = rng.uniform(x[0] - 1, x[-1] + 1, 333).astype(dt)
-    for nyi in (1000, 777):                      # even: 2-wide stores, odd: scalar stores
+    for nyi in (1000, 1002, 777):                # multiple of 4: 32-byte stores, even: 16-byte, odd: scalar
         yi = rng.uniform(-2.1, 3.1, nyi).astype(dt)
         assert same_bits(plan.grid(xi, yi, extrap=0.5), oracle.interp2_grid(x, y, z, xi, yi, extrap=0.5, nthreads=8))
 
