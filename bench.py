@@ -291,7 +291,7 @@ def main():
                        "grid": "4096x4096 float64 column-major (128 MiB), seed 2234",
                        "queries": "1e8 (x,y) ~ U[0,1]^2 per GPU, unsorted, seed 2235+rank",
                        "l2": "inputs larger than L2 (1.6 GB of queries + 0.8 GB of outputs per step)",
-                       "layout": "axes staged in shared memory by TMA bulk copy; Z as 2x2 corner records (512 MiB)",
+                       "layout": "linspace axes recognised as affine at plan time (knots recomputed in registers; other axes are staged in shared memory by TMA bulk copy); Z as 2x2 corner records (512 MiB)",
                        "parallelism": f"query shards x{n_gpus}, no collective"},
             "gpu_launches": args.steps,
             "clocks": clocks,
@@ -374,6 +374,24 @@ def main():
             gb = (8 * 1e8 + ALG_BYTES_GRID + 16 * 1e4) / (msg * 1e-3) / 1e9
             extra["interp2_grid_f64_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msg * 1e-3), "ms_per_launch": msg,
                                                  "algorithmic_GBps": gb, "roofline_frac": gb / peak}
+            # configs[1] through the opt-in L2-banded pipeline (partition by record band -> band-major
+            # interpolation -> un-permute; profiles/interp2_banded_r1.md): same queries, same bits
+            pb = B.Interp2Plan(*grid, flags=B.Interp2Plan.FORCE_BANDS)
+            zb = torch.empty_like(zq)
+            nbd = max(5, args.steps // 2)
+            msb = time_steps(torch, lambda: pb.scattered(xq, yq, out=zb), nbd, 3, dist) / nbd
+            plan.scattered(xq, yq, out=zq)
+            same = bool(torch.equal(zb.view(torch.int64), zq.view(torch.int64)))
+            extra["interp2_scattered_f64_banded_pipeline_opt_in"] = {
+                "points_per_s": n_gpus * NQ / (msb * 1e-3), "ms_per_call": msb, "kernels_per_call": 3,
+                "algorithmic_GBps": alg_bytes / (msb * 1e-3) / 1e9, "roofline_frac": alg_bytes / (msb * 1e-3) / 1e9 / peak,
+                "bitwise_equal_to_direct_kernel": same}
+            pb.close(); del zb
+            # write-only ceiling of this GPU (a kernel that only stores): what the grid kernel is up against
+            wbuf = torch.empty(NQ, dtype=torch.float64, device="cuda")
+            msw = time_steps(torch, lambda: wbuf.fill_(1.5), 10, 3, dist) / 10
+            extra["write_only_ceiling_GBps"] = 8 * NQ / (msw * 1e-3) / 1e9
+            del wbuf
             # configs[1] with tile-sorted queries (SURVEY 8d variant iii): same points, ordered by grid cell
             cell = (xq * (NX - 1)).floor().to(torch.int64) * NY + (yq * (NY - 1)).floor().to(torch.int64)
             order = cell.argsort()
