@@ -190,7 +190,7 @@ def test_interp2_layout_flags_give_identical_bits(b200, oracle):
     xq = rng.uniform(-0.1, 1.1, 100_000); yq = rng.uniform(-0.1, 1.1, 100_000)
     ref = oracle.interp2_scattered(x, y, z, xq, yq, extrap=1.5)
     L = _lib.lib()
-    for flags in (1, 2):   # B200_INTERP2_NO_CELLS, B200_INTERP2_FORCE_CELLS
+    for flags in (1, 2, 32):   # B200_INTERP2_NO_CELLS, B200_INTERP2_FORCE_CELLS, B200_INTERP2_FORCE_TILES
         h = C.c_void_p()
         _lib.check(L.b200_interp2_plan_create_ex(0, x.ctypes.data_as(C.c_void_p), C.c_size_t(x.size), y.ctypes.data_as(C.c_void_p),
                                                  C.c_size_t(y.size), z.ctypes.data_as(C.c_void_p), C.c_uint(flags), C.byref(h)))
@@ -267,3 +267,22 @@ def test_interp2_affine_axes_same_bits(b200, oracle, monkeypatch):
         monkeypatch.setenv("B200_INTERP_AFFINE", affine)
         for flags in (0, b200.Interp2Plan.FORCE_CELLS, b200.Interp2Plan.NO_CELLS):
             assert same_bits(b200.Interp2Plan(x, y, z, flags=flags).scattered(xq, yq, extrap=-4.0), ref)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(513, 384), (4, 4), (2, 2), (3, 7), (10, 5), (301, 299)])
+def test_interp2_tile_layout_same_bits(b200, oracle, dt, shape):
+    """Overlapping 4x4 tiles (B200_INTERP2_FORCE_TILES): every cell's corners in one 128-byte line.
+    Grid sizes around the tile stride (3) exercise the clamped last row / column of tiles."""
+    nx, ny = shape
+    rng = np.random.default_rng(20)
+    x = np.unique(np.cumsum(0.5 + rng.random(nx)).astype(dt)); y = np.linspace(-2, 3, ny).astype(dt)
+    z = rng.standard_normal((y.size, x.size)).astype(dt)
+    plan = b200.Interp2Plan(x, y, z, flags=b200.Interp2Plan.FORCE_TILES)
+    nq = 200_003
+    xq = rng.uniform(x[0] - 0.5, x[-1] + 0.5, nq).astype(dt); yq = rng.uniform(-2.1, 3.1, nq).astype(dt)
+    xq[:5] = [x[0], x[-1], np.nan, x[1], x[-1]]; yq[:5] = [y[0], y[-1], 0.0, np.nan, y[0]]
+    xq[5:5 + x.size] = x; yq[5:5 + x.size] = y[-1]              # every x knot on the last row
+    xq[1000:1000 + y.size] = x[-1]; yq[1000:1000 + y.size] = y   # every y knot on the last column
+    for extrap in (np.nan, -1.5):
+        assert same_bits(plan.scattered(xq, yq, extrap=extrap), oracle.interp2_scattered(x, y, z, xq, yq, extrap=extrap, nthreads=8))

@@ -11,7 +11,12 @@ template<int MODE> __global__ void gather(const double* __restrict__ tab, size_t
     if (MODE==0) asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];":"=d"(a),"=d"(b),"=d"(c),"=d"(d):"l"(p));
     else if (MODE==1) { asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];":"=d"(a),"=d"(b):"l"(p)); asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];":"=d"(c),"=d"(d):"l"(p+2)); }
     else if (MODE==2) { asm volatile("ld.global.nc.f64 %0, [%1];":"=d"(a):"l"(p)); b=c=d=0; }
-    else { asm volatile("ld.global.cv.f64 %0, [%1];":"=d"(a):"l"(p)); b=c=d=0; }
+    else if (MODE==3) { asm volatile("ld.global.cv.f64 %0, [%1];":"=d"(a):"l"(p)); b=c=d=0; }
+    else if (MODE==4) asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f64 {%0,%1,%2,%3}, [%4];":"=d"(a),"=d"(b),"=d"(c),"=d"(d):"l"(p));
+    else if (MODE==5) asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4];":"=d"(a),"=d"(b),"=d"(c),"=d"(d):"l"(p));
+    else if (MODE==6) asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f64 {%0,%1,%2,%3}, [%4];":"=d"(a),"=d"(b),"=d"(c),"=d"(d):"l"(p));
+    else if (MODE==7) asm volatile("ld.global.L1::no_allocate.L2::evict_first.L2::64B.v4.f64 {%0,%1,%2,%3}, [%4];":"=d"(a),"=d"(b),"=d"(c),"=d"(d):"l"(p));
+    else { asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];":"=d"(a):"l"(p)); b=c=d=0; }
     out[i]=a+b+c+d;
   }
 }
@@ -24,7 +29,8 @@ int main(int argc,char**argv){
   cudaEvent_t e0,e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for(int rep=0;rep<3;rep++){
     cudaEventRecord(e0);
-    if(mode==0) gather<0><<<148*16,256>>>(tab,nrec,out,nq); else if(mode==1) gather<1><<<148*16,256>>>(tab,nrec,out,nq); else if(mode==2) gather<2><<<148*16,256>>>(tab,nrec,out,nq); else gather<3><<<148*16,256>>>(tab,nrec,out,nq);
+    switch(mode){case 0: gather<0><<<148*16,256>>>(tab,nrec,out,nq); break; case 1: gather<1><<<148*16,256>>>(tab,nrec,out,nq); break; case 2: gather<2><<<148*16,256>>>(tab,nrec,out,nq); break; case 3: gather<3><<<148*16,256>>>(tab,nrec,out,nq); break;
+      case 4: gather<4><<<148*16,256>>>(tab,nrec,out,nq); break; case 5: gather<5><<<148*16,256>>>(tab,nrec,out,nq); break; case 6: gather<6><<<148*16,256>>>(tab,nrec,out,nq); break; case 7: gather<7><<<148*16,256>>>(tab,nrec,out,nq); break; default: gather<8><<<148*16,256>>>(tab,nrec,out,nq);}
     cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms,e0,e1);
     printf("mode %d gran %d: %.3f ms  %.2f Ggather/s\n",mode,gran,ms,nq/ms/1e6);
   }

@@ -34,7 +34,7 @@ yq = torch.rand(nq, generator=g, device="cuda", dtype=torch.float64)
 outs = {}
 for affine in ("1", "0"):
     os.environ["B200_INTERP_AFFINE"] = affine
-    for name, flags in (("direct", 4), ("banded", 8)):
+    for name, flags in (("records", 4 | 16), ("tiles", 4 | 32), ("banded", 8)):
         plan = B.Interp2Plan(x, y, z, flags=flags)
         zq = torch.empty_like(xq)
         for _ in range(3): plan.scattered(xq, yq, out=zq)
@@ -46,5 +46,5 @@ for affine in ("1", "0"):
         print(f"affine={affine} {name}: {e0.elapsed_time(e1) / 10:.3f} ms per 1e8 queries", flush=True)
         outs[name + affine] = zq.clone()
         plan.close()
-ref = outs["direct0"].view(torch.int64)
+ref = outs["records0"].view(torch.int64)
 print("all four bitwise equal:", all(torch.equal(ref, v.view(torch.int64)) for v in outs.values()))
