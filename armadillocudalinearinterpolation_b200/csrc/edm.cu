@@ -997,8 +997,13 @@ int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaSt
   // 128-thread CTAs capped at 64 registers: 8 rings resident per SM, i.e. 8 serial Newton
   // chains overlapping (measured: 5.9 -> 4.5 ms per default evaluation vs 4 rings at 118 regs)
   const bool full = (h->N == threads * (unsigned)NPT);  // no ragged tail: bounds checks compiled out
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   if (threads <= 128) {
-    if (full) B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8, true>));
+    // Few rings (one wave even at 4 per SM): the uncapped build (116 registers, no spills) has the shorter
+    // serial chain — 2.34 instead of 2.81 ms for a default ring (profiles/edm_evolve_r1.md).
+    if (full && nitems <= (size_t)sms * 4) B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 4, true>));
+    else if (full) B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8, true>));
     else B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8, false>));
   } else if (threads <= 256) {
     B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 256, 2, false>));
