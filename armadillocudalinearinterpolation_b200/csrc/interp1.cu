@@ -236,9 +236,11 @@ int plan1_launch(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* i
     if (idx) B200_TRY(launch(interp1_smem_kernel<T, true>));
     else B200_TRY(launch(interp1_smem_kernel<T, false>));
   } else if (nvec) {
-    // two waves of 8 resident CTAs per SM, grid-stride beyond that (measured at 1e7 queries: x16 37.0 us, x64 38.9 us)
+    // a few waves of 8 resident CTAs per SM, grid-stride beyond that
     size_t blocks = (nvec + kThreads - 1) / kThreads;
-    static const size_t mult = [] { const char* e = getenv("B200_INTERP1_GRID_MULT"); return (size_t)(e && atoi(e) > 0 ? atoi(e) : 16); }();
+    // measured: 1e7 queries 37.0 us with 16 CTAs per SM vs 38.9 us with 64; 1e8 queries 0.304 ms with 64 vs 0.316 ms with 16
+    static const size_t forced = [] { const char* e = getenv("B200_INTERP1_GRID_MULT"); return (size_t)(e && atoi(e) > 0 ? atoi(e) : 0); }();
+    const size_t mult = forced ? forced : (blocks > (size_t)148 * 256 ? 64 : 16);
     int grid = (int)(blocks < (size_t)148 * mult ? blocks : (size_t)148 * mult);
     if (idx) interp1_vec_kernel<T, true><<<grid, kThreads, 0, st>>>(ax, seg, xi, yi, idx, nvec, extrap);
     else interp1_vec_kernel<T, false><<<grid, kThreads, 0, st>>>(ax, seg, xi, yi, nullptr, nvec, extrap);
