@@ -1002,7 +1002,11 @@ int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaSt
   if (threads <= 128) {
     // Few rings (one wave even at 4 per SM): the uncapped build (116 registers, no spills) has the shorter
     // serial chain — 2.34 instead of 2.81 ms for a default ring (profiles/edm_evolve_r1.md).
-    if (full && nitems <= (size_t)sms * 4) B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 4, true>));
+    bool done = false;
+    if constexpr (NPT == 8) {   // (only the default 8 neurons/thread gets the second build: compile time)
+      if (full && nitems <= (size_t)sms * 4) { B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 4, true>)); done = true; }
+    }
+    if (done) {}
     else if (full) B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8, true>));
     else B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8, false>));
   } else if (threads <= 256) {
