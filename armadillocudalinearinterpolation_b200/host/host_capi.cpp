@@ -4,6 +4,7 @@
 #include <cstring>
 #include <sstream>
 #include "EventDrivenMapB200.hpp"
+#include "InterpB200.hpp"
 #include "NewtonSolver.hpp"
 #include "Stability.hpp"
 
@@ -146,6 +147,55 @@ int b200_host_edm_stability(double beta, unsigned R, unsigned N, const double* u
     arma::cx_vec w = st.ComputeEigenvalues(u);
     for (int i = 0; i < n; ++i) { eig_re[i] = w(i).real(); eig_im[i] = w(i).imag(); }
     return st.ComputeNumUnstableEigenvalues(u);
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+
+// ---- the Armadillo-facing interpolation adaptor (InterpB200.hpp), driven like a C++ user would ----
+// mode 0: b200::interp1 (one-shot), 1: Interp1Plan + SetValues(y2) (y2 may be NULL)
+int b200_host_interp1(const double* x, const double* y, int n, const double* xi, int ni, double* yi, double extrap,
+                      const char* method, int mode, const double* y2) {
+  try {
+    arma::vec X(n), Y(n), XI(ni), YI;
+    for (int i = 0; i < n; ++i) { X(i) = x[i]; Y(i) = y[i]; }
+    for (int i = 0; i < ni; ++i) XI(i) = xi[i];
+    if (mode == 0) b200::interp1(X, Y, XI, YI, method, extrap);
+    else {
+      b200::Interp1Plan plan(X, Y);
+      if (y2) { arma::vec Y2(n); for (int i = 0; i < n; ++i) Y2(i) = y2[i]; plan.SetValues(Y2); }
+      plan(XI, YI, extrap);
+    }
+    if ((int)YI.n_elem != ni) { g_err = "YI has the wrong size"; return -1; }
+    for (int i = 0; i < ni; ++i) yi[i] = YI(i);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// mode 0: b200::interp2 (tensor grid, zi is nyi x nxi column-major), 1: Interp2Plan::Grid,
+// 2: Interp2Plan::Scattered (nxi == nyi queries, zi has nxi entries)
+int b200_host_interp2(const double* x, int nx, const double* y, int ny, const double* z_colmajor, const double* xi, int nxi,
+                      const double* yi, int nyi, double* zi, double extrap, int mode) {
+  try {
+    arma::vec X(nx), Y(ny), XI(nxi), YI(nyi);
+    arma::mat Z(ny, nx);
+    for (int i = 0; i < nx; ++i) X(i) = x[i];
+    for (int i = 0; i < ny; ++i) Y(i) = y[i];
+    for (int i = 0; i < nx * ny; ++i) Z.memptr()[i] = z_colmajor[i];
+    for (int i = 0; i < nxi; ++i) XI(i) = xi[i];
+    for (int i = 0; i < nyi; ++i) YI(i) = yi[i];
+    if (mode == 2) {
+      arma::vec ZQ;
+      b200::Interp2Plan plan(X, Y, Z);
+      plan.Scattered(XI, YI, ZQ, extrap);
+      for (int i = 0; i < nxi; ++i) zi[i] = ZQ(i);
+      return 0;
+    }
+    arma::mat ZI;
+    if (mode == 0) b200::interp2(X, Y, Z, XI, YI, ZI, "linear", extrap);
+    else { b200::Interp2Plan plan(X, Y, Z); plan.Grid(XI, YI, ZI, extrap); }
+    if ((int)ZI.n_rows != nyi || (int)ZI.n_cols != nxi) { g_err = "ZI has the wrong shape"; return -1; }
+    for (int i = 0; i < nxi * nyi; ++i) zi[i] = ZI.memptr()[i];
+    return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 

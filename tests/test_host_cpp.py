@@ -163,3 +163,52 @@ def test_continuation_driver_runs(host):
     assert len(lines) == 2
     assert all("unstable eigenvalues = 1" in l for l in lines), lines
     assert out.stdout.count("The method converged after") == 2
+
+
+# ---- the Armadillo-facing interpolation adaptor (host/InterpB200.hpp) ----
+def test_interp_adaptor_rejects_what_it_does_not_offer(host):
+    """No GPU needed: argument checks of b200::interp1 happen before any device call
+    (arma::interp1 raises logic_error for unknown methods and mismatched X / Y too)."""
+    x = np.linspace(0, 1, 8); y = x ** 2; xi = np.array([0.5]); yi = np.zeros(1)
+    rc = host.b200_host_interp1(dp(x), dp(y), 8, dp(xi), 1, dp(yi), C.c_double(0.0), b"nearest", 0, None)
+    assert rc == -1 and b"unsupported interpolation type" in host.b200_host_last_error()
+    for name in ("b200_host_interp1", "b200_host_interp2"):
+        assert hasattr(host, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_interp1_adaptor_matches_oracle(host, oracle, mode):
+    rng = np.random.default_rng(31)
+    x = np.cumsum(0.5 + rng.random(3000)); y = np.sin(x); y2 = np.cos(x)
+    xi = rng.uniform(x[0] - 1, x[-1] + 1, 20001); xi[:3] = [x[0], x[-1], np.nan]
+    yi = np.empty_like(xi)
+    for method in (b"linear", b"*linear"):
+        rc = host.b200_host_interp1(dp(x), dp(y), x.size, dp(xi), xi.size, dp(yi), C.c_double(-2.5), method, mode,
+                                    dp(y2) if mode == 1 else None)
+        assert rc == 0, host.b200_host_last_error()
+        ref = oracle.interp1(x, y2 if mode == 1 else y, xi, extrap=-2.5, want_idx=False)
+        assert np.array_equal(np.isnan(yi), np.isnan(ref)) and np.array_equal(yi[~np.isnan(yi)], ref[~np.isnan(ref)])
+    xs = x.copy(); xs[5] = xs[4]                                       # not strictly ascending: reported, not sorted
+    assert host.b200_host_interp1(dp(xs), dp(y), x.size, dp(xi), xi.size, dp(yi), C.c_double(0.0), b"linear", 0, None) == -1
+    assert b"ascending" in host.b200_host_last_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_interp2_adaptor_matches_oracle(host, oracle, mode):
+    rng = np.random.default_rng(32)
+    x = np.linspace(0, 1, 70); y = np.cumsum(0.5 + rng.random(50)); z = np.asfortranarray(rng.standard_normal((50, 70)))
+    if mode == 2:
+        xq = rng.uniform(-0.1, 1.1, 5000); yq = rng.uniform(y[0] - 1, y[-1] + 1, 5000)
+        out = np.empty(5000)
+        rc = host.b200_host_interp2(dp(x), 70, dp(y), 50, dp(z), dp(xq), 5000, dp(yq), 5000, dp(out), C.c_double(7.0), mode)
+        assert rc == 0, host.b200_host_last_error()
+        ref = oracle.interp2_scattered(x, y, z, xq, yq, extrap=7.0)
+    else:
+        xi = np.sort(rng.uniform(-0.1, 1.1, 40)); yi = np.sort(rng.uniform(y[0] - 1, y[-1] + 1, 33))
+        out = np.empty((33, 40), order="F")
+        rc = host.b200_host_interp2(dp(x), 70, dp(y), 50, dp(z), dp(xi), 40, dp(yi), 33, dp(out), C.c_double(7.0), mode)
+        assert rc == 0, host.b200_host_last_error()
+        ref = oracle.interp2_grid(x, y, z, xi, yi, extrap=7.0)
+    assert out.shape == ref.shape and np.array_equal(out, ref)
