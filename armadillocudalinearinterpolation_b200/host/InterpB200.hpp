@@ -60,6 +60,26 @@ inline void interp2(const arma::vec& X, const arma::vec& Y, const arma::mat& Z, 
                                  YI.memptr(), YI.n_elem, ZI.memptr(), extrapolation_value));
 }
 
+// arma::fvec / arma::fmat overloads (FP32 arithmetic throughout, same rule)
+inline void interp1(const arma::fvec& X, const arma::fvec& Y, const arma::fvec& XI, arma::fvec& YI,
+                    const char* method = "linear", const float extrapolation_value = (float)arma::datum::nan) {
+  detail::check_method(method);
+  if (X.n_elem != Y.n_elem) throw std::logic_error("b200::interp1: X and Y must have the same number of elements");
+  YI.set_size(XI.n_elem);
+  detail::check(b200_interp1_f32(X.memptr(), Y.memptr(), X.n_elem, XI.memptr(), XI.n_elem, YI.memptr(), NULL,
+                                 extrapolation_value));
+}
+inline void interp2(const arma::fvec& X, const arma::fvec& Y, const arma::fmat& Z, const arma::fvec& XI,
+                    const arma::fvec& YI, arma::fmat& ZI, const char* method = "linear",
+                    const float extrapolation_value = (float)arma::datum::nan) {
+  detail::check_method(method);
+  if (X.n_elem != Z.n_cols || Y.n_elem != Z.n_rows)
+    throw std::logic_error("b200::interp2: X.n_elem must equal Z.n_cols and Y.n_elem must equal Z.n_rows");
+  ZI.set_size(YI.n_elem, XI.n_elem);
+  detail::check(b200_interp2_f32(X.memptr(), X.n_elem, Y.memptr(), Y.n_elem, Z.memptr(), XI.memptr(), XI.n_elem,
+                                 YI.memptr(), YI.n_elem, ZI.memptr(), extrapolation_value));
+}
+
 // Grid resident in HBM: one upload, many query batches (host buffers; pinned ones — b200_host_alloc — overlap best).
 class Interp1Plan {
  public:

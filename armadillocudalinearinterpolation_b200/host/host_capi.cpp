@@ -171,6 +171,18 @@ int b200_host_interp1(const double* x, const double* y, int n, const double* xi,
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// arma::fvec overload of b200::interp1
+int b200_host_interp1_f32(const float* x, const float* y, int n, const float* xi, int ni, float* yi, float extrap) {
+  try {
+    arma::fvec X(n), Y(n), XI(ni), YI;
+    for (int i = 0; i < n; ++i) { X(i) = x[i]; Y(i) = y[i]; }
+    for (int i = 0; i < ni; ++i) XI(i) = xi[i];
+    b200::interp1(X, Y, XI, YI, "*linear", extrap);
+    for (int i = 0; i < ni; ++i) yi[i] = YI(i);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // mode 0: b200::interp2 (tensor grid, zi is nyi x nxi column-major), 1: Interp2Plan::Grid,
 // 2: Interp2Plan::Scattered (nxi == nyi queries, zi has nxi entries)
 int b200_host_interp2(const double* x, int nx, const double* y, int ny, const double* z_colmajor, const double* xi, int nxi,

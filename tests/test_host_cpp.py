@@ -212,3 +212,13 @@ def test_interp2_adaptor_matches_oracle(host, oracle, mode):
         assert rc == 0, host.b200_host_last_error()
         ref = oracle.interp2_grid(x, y, z, xi, yi, extrap=7.0)
     assert out.shape == ref.shape and np.array_equal(out, ref)
+
+
+@pytest.mark.gpu
+def test_interp1_adaptor_fvec(host, oracle):
+    rng = np.random.default_rng(33)
+    x = np.unique(np.cumsum(0.5 + rng.random(2000)).astype(np.float32)); y = np.sin(x).astype(np.float32)
+    xi = rng.uniform(x[0], x[-1], 10001).astype(np.float32)
+    yi = np.empty_like(xi)
+    assert host.b200_host_interp1_f32(dp(x), dp(y), x.size, dp(xi), xi.size, dp(yi), C.c_float(0.0)) == 0, host.b200_host_last_error()
+    assert np.array_equal(yi, oracle.interp1(x, y, xi, extrap=0.0, want_idx=False))
