@@ -32,6 +32,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NX = NY = 4096
+METRIC = "interp points/s (2-D bilinear, 4096x4096 f64 grid, 1e8 scattered queries)"   # both arms
+WORKLOAD = "interp2_scattered_f64_4096x4096_1e8_queries_per_gpu"
+GRID_DESC = "4096x4096 float64 column-major (128 MiB), seed 2234"
 NQ = 100_000_000
 ALG_BYTES_PER_QUERY = 24            # xq, yq in + zq out, float64
 ALG_BYTES_GRID = 8 * NX * NY        # the grid is read once
@@ -148,11 +151,11 @@ def run_reference(args):
         cpu_interp2(2_000_000, threads, grid)
     vals = [cpu_interp2(sample, threads, grid) for _ in range(max(1, min(args.steps, 5)))]
     v = float(np.mean(vals))
-    line = {"impl": "reference", "metric": "interp points/s (2-D bilinear, 4096x4096 f64 grid, scattered queries)",
+    line = {"impl": "reference", "metric": METRIC,
             "value": v, "unit": "points/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1,
             "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "interp2_scattered_f64_4096x4096", "sample": f"{sample} queries per step (of 1e8)"},
+            "config": {"workload": WORKLOAD, "grid": GRID_DESC, "sample": f"{sample} queries per step (of 1e8)"},
             "cpu_baseline": {"value": v, "unit": "points/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} of 1e8 scattered queries, OpenMP over queries"},
             "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -285,12 +288,12 @@ def main():
     g2_ms, g2_rate = L_.bench_random_gather(tile_bytes, NQ)
     fp64_peak = L_.bench_fp64_fma()
 
-    line = {"metric": "interp points/s (2-D bilinear, 4096x4096 f64 grid, 1e8 scattered queries)",
+    line = {"metric": METRIC,
             "value": value, "unit": "points/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "interp2_scattered_f64_4096x4096_1e8_queries_per_gpu",
-                       "grid": "4096x4096 float64 column-major (128 MiB), seed 2234",
+            "config": {"workload": WORKLOAD,
+                       "grid": GRID_DESC,
                        "queries": "1e8 (x,y) ~ U[0,1]^2 per GPU, unsorted, seed 2235+rank",
                        "l2": "inputs larger than L2 (1.6 GB of queries + 0.8 GB of outputs per step)",
                        "layout": "linspace axes recognised as affine at plan time (knots recomputed in registers; other axes are staged in shared memory by TMA bulk copy); Z as overlapping 4x4 tiles, one 128-byte line per cell (228 MiB)",
