@@ -34,12 +34,6 @@ struct BandDev {
   uint32_t chunk;     // queries per chunk (2048 or 4096)
 };
 
-__device__ __forceinline__ unsigned lanemask_lt() {
-  unsigned m;
-  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-  return m;
-}
-
 // four consecutive queries of a thread: one 256-bit (f64) / 128-bit (f32) streaming load when the
 // array is 32-byte aligned and the four are inside the slab, guarded scalar loads otherwise
 __device__ __forceinline__ void band_load4(const double* p, size_t i, size_t nq, bool vec, double (&v)[4]) {
