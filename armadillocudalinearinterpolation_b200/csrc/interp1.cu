@@ -114,7 +114,8 @@ interp1_scalar_kernel(AxisDev<T> ax, const T* __restrict__ seg, const T* __restr
 // The "coarse profile -> fine ensemble" case (a few thousand knots, millions of queries): persistent
 // CTAs copy the knots, the values and (for non-uniform knots) the bucket table into shared memory
 // once with TMA bulk copies and then stream queries; the bracket lookup and the two value reads never
-// leave the SM, so HBM carries exactly 16 bytes (f64) per query.
+// leave the SM, so HBM carries exactly 16 bytes (f64) per query.  Affine knots (linspace) are recomputed
+// instead of staged: half the shared memory, half the bank-conflicted look-ups (0.79 vs 0.74 of peak).
 constexpr int kSmem1Threads = 512;
 
 template <typename T, bool WANT_IDX>
@@ -125,26 +126,27 @@ interp1_smem_kernel(AxisDev<T> ax, const T* __restrict__ yg, const T* __restrict
   constexpr int V = Vec256<T>::n;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem1);
   auto pad16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  const size_t xb_bytes = pad16(sizeof(T) * ax.n);
-  const size_t fb_bytes = ax.mode ? pad16(sizeof(int32_t) * ((size_t)ax.nb + 1)) : 0;
+  const size_t yb_bytes = pad16(sizeof(T) * ax.n);
+  const size_t xb_bytes = ax.affine ? 0 : yb_bytes;   // affine knots are recomputed: only the values are staged
+  const size_t fb_bytes = (!ax.affine && ax.mode) ? pad16(sizeof(int32_t) * ((size_t)ax.nb + 1)) : 0;
   T* sx = reinterpret_cast<T*>(smem1 + 16);
   T* sy = reinterpret_cast<T*>(smem1 + 16 + xb_bytes);
-  int32_t* sf = reinterpret_cast<int32_t*>(smem1 + 16 + 2 * xb_bytes);
+  int32_t* sf = reinterpret_cast<int32_t*>(smem1 + 16 + xb_bytes + yb_bytes);
   if (threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (unsigned)(2 * xb_bytes + fb_bytes));
+    mbar_expect_tx(bar, (unsigned)(xb_bytes + yb_bytes + fb_bytes));
     const unsigned chunk = 16384;
     auto copy = [&](void* dst, const void* src, size_t bytes) {
       for (size_t o = 0; o < bytes; o += chunk)
         tma_bulk_g2s((unsigned char*)dst + o, (const unsigned char*)src + o, (unsigned)(bytes - o < chunk ? bytes - o : chunk), bar);
     };
-    copy(sx, ax.x, xb_bytes);
-    copy(sy, yg, xb_bytes);
+    if (xb_bytes) copy(sx, ax.x, xb_bytes);
+    copy(sy, yg, yb_bytes);
     if (fb_bytes) copy(sf, ax.first, fb_bytes);
   }
   mbar_wait(bar, 0);
-  const AxisSmem<T> A = {sx, sf, ax.x0, ax.xmax, ax.inv_w, ax.n, ax.nb, ax.mode, 0, (T)0};
+  const AxisSmem<T> A = {sx, sf, ax.x0, ax.xmax, ax.inv_w, ax.n, ax.nb, ax.mode, ax.affine, ax.step};
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     T q[V], y[V];
@@ -227,7 +229,8 @@ int plan1_create(b200_interp1_plan* p, const T* xg, const T* yg, size_t ng) {
   {
     auto pad16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
     const AxisDev<T>& ax = axis_of<T>(p).dev;
-    const size_t need = 16 + 2 * pad16(sizeof(T) * ng) + (ax.mode ? pad16(sizeof(int32_t) * ((size_t)ax.nb + 1)) : 0);
+    const size_t need = 16 + (ax.affine ? 1 : 2) * pad16(sizeof(T) * ng) +
+                        ((!ax.affine && ax.mode) ? pad16(sizeof(int32_t) * ((size_t)ax.nb + 1)) : 0);
     const char* e = getenv("B200_INTERP1_SMEM");
     p->smem_bytes = (need <= 100 * 1024 && !(e && e[0] == '0')) ? need : 0;   // two CTAs per SM
   }
