@@ -31,10 +31,6 @@ template <typename T> struct Loader1;
 template <> struct Loader1<double> { using type = LoadSeg1D; };
 template <> struct Loader1<float> { using type = LoadSeg1F; };
 
-template <typename T> struct LoaderPair;
-template <> struct LoaderPair<double> { using type = LoadPairD; };
-template <> struct LoaderPair<float> { using type = LoadPairF; };
-
 template <typename T>
 __device__ __forceinline__ T interp1_one(const AxisDev<T>& ax, const typename Loader1<T>::type& ld,
                                          T q, T extrap, int32_t& idx) {
@@ -54,36 +50,21 @@ template <> __device__ __forceinline__ LoadSeg1F make_loader1<float>(const float
 
 // Vector kernel: each thread owns 32 bytes of queries per iteration (4 doubles / 8 floats),
 // i.e. V independent gather chains in flight.  Requires 32-byte aligned xi / yi.
-// AFF: the knots are an exact arithmetic function of their index (AxisDev::affine), so the bracket needs no
-// memory at all and the gather shrinks from the 32-byte segment record to the 16-byte value pair (y[a], y[a+1]).
-template <typename T, bool WANT_IDX, bool AFF>
+// (Affine axes could gather the 16-byte value pair instead of the 32-byte record; measured within +-2 %
+// of this kernel at 1e7 and 1e8 queries — the gather RATE bounds it, not the bytes — and not kept.)
+template <typename T, bool WANT_IDX>
 __global__ void __launch_bounds__(kThreads)
-interp1_vec_kernel(AxisDev<T> ax, const T* __restrict__ seg, const T* __restrict__ ypair, const T* __restrict__ xi,
+interp1_vec_kernel(AxisDev<T> ax, const T* __restrict__ seg, const T* __restrict__ xi,
                    T* __restrict__ yi, int32_t* __restrict__ idx, size_t nvec, T extrap) {
   constexpr int V = Vec256<T>::n;
   const auto ld = make_loader1<T>(seg);
-  const typename LoaderPair<T>::type ldp = {ypair, l2_policy_evict_last()};
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     T q[V], y[V];
     int32_t id[V];
     ld_stream_256(xi + i * V, q);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      if (AFF) {
-        const T qq = q[j];
-        if (!(qq >= ax.x0 && qq <= ax.xmax)) { id[j] = -1; y[j] = (qq != qq) ? qnan<T>() : extrap; }
-        else {
-          T xa, xb;
-          const int a = affine_bracket<T>(ax.affine, ax.x0, ax.step, ax.xmax, ax.n, bin_of(ax, qq), qq, xa, xb);
-          const Pair<T> yy = ldp(a);   // (y[a], y[min(a+1, n-1)])
-          id[j] = a;
-          y[j] = blend(weight_of(xa, xb, qq), yy.xa, yy.xb);
-        }
-      } else {
-        y[j] = interp1_one<T>(ax, ld, q[j], extrap, id[j]);
-      }
-    }
+    for (int j = 0; j < V; ++j) y[j] = interp1_one<T>(ax, ld, q[j], extrap, id[j]);
     st_stream_256(yi + i * V, y);
     if (WANT_IDX) {
       if (V == 8) {
@@ -185,7 +166,6 @@ struct b200_interp1_plan {
   Axis<float> ax32;
   void* yg = nullptr;   // device copy of the values
   void* seg = nullptr;  // [ng][4] segment records
-  void* ypair = nullptr;  // [ng][2] (y[a], y[a+1]): affine axes gather this instead of the records
   size_t smem_bytes = 0;  // > 0: the grid fits the shared-memory path
   cudaStream_t stream[2] = {nullptr, nullptr};
   // staging for host-buffer execution (allocated on first use)
@@ -207,7 +187,6 @@ int plan1_build_seg(b200_interp1_plan* p, cudaStream_t st) {
   Axis<T>& A = axis_of<T>(p);
   build_seg1_kernel<T><<<grid_for(p->ng), kThreads, 0, st>>>(A.x, (const T*)p->yg, (int)p->ng,
                                                              (T*)p->seg);
-  if (p->ypair) build_pair_kernel<T><<<grid_for(p->ng), kThreads, 0, st>>>((const T*)p->yg, (int)p->ng, (T*)p->ypair);
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -222,7 +201,6 @@ int plan1_create(b200_interp1_plan* p, const T* xg, const T* yg, size_t ng) {
   B200_CUDA(cudaMalloc(&p->yg, ng * sizeof(T) + 16));  // +16: bulk copies move whole 16-byte units
   B200_CUDA(cudaMemsetAsync(p->yg, 0, ng * sizeof(T) + 16, p->stream[0]));
   B200_CUDA(cudaMalloc(&p->seg, ng * 4 * sizeof(T)));
-  if (axis_of<T>(p).dev.affine) B200_CUDA(cudaMalloc(&p->ypair, ng * 2 * sizeof(T)));
   B200_CUDA(cudaMemcpyAsync(p->yg, yg, ng * sizeof(T), cudaMemcpyHostToDevice, p->stream[0]));
   B200_TRY(plan1_build_seg<T>(p, p->stream[0]));
   B200_CUDA(cudaStreamSynchronize(p->stream[0]));
@@ -269,14 +247,8 @@ int plan1_launch(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* i
     static const size_t forced = [] { const char* e = getenv("B200_INTERP1_GRID_MULT"); return (size_t)(e && atoi(e) > 0 ? atoi(e) : 0); }();
     const size_t mult = forced ? forced : (blocks > (size_t)148 * 256 ? 64 : 16);
     int grid = (int)(blocks < (size_t)148 * mult ? blocks : (size_t)148 * mult);
-    const T* yp = (const T*)p->ypair;
-    if (yp && ax.affine) {
-      if (idx) interp1_vec_kernel<T, true, true><<<grid, kThreads, 0, st>>>(ax, seg, yp, xi, yi, idx, nvec, extrap);
-      else interp1_vec_kernel<T, false, true><<<grid, kThreads, 0, st>>>(ax, seg, yp, xi, yi, nullptr, nvec, extrap);
-    } else {
-      if (idx) interp1_vec_kernel<T, true, false><<<grid, kThreads, 0, st>>>(ax, seg, yp, xi, yi, idx, nvec, extrap);
-      else interp1_vec_kernel<T, false, false><<<grid, kThreads, 0, st>>>(ax, seg, yp, xi, yi, nullptr, nvec, extrap);
-    }
+    if (idx) interp1_vec_kernel<T, true><<<grid, kThreads, 0, st>>>(ax, seg, xi, yi, idx, nvec, extrap);
+    else interp1_vec_kernel<T, false><<<grid, kThreads, 0, st>>>(ax, seg, xi, yi, nullptr, nvec, extrap);
   }
   size_t done = nvec * V;
   if (done < ni) {
@@ -341,7 +313,6 @@ void plan1_free(b200_interp1_plan* p) {
   p->ax32.release();
   cudaFree(p->yg);
   cudaFree(p->seg);
-  cudaFree(p->ypair);
   for (int s = 0; s < 2; ++s) {
     cudaFree(p->st_in[s]); cudaFree(p->st_out[s]); cudaFree(p->st_idx[s]);
     if (p->stream[s]) cudaStreamDestroy(p->stream[s]);
