@@ -1,6 +1,8 @@
 """interp2 grid kernel: rows per thread (B200_INTERP2_GRID_V) and the write-only ceiling of the GPU."""
 import os, sys
 sys.path.insert(0, "/root/repo")
+from armadillocudalinearinterpolation_b200 import _lib
+if len(sys.argv) > 1: _lib.LIB_PATH = sys.argv[1]
 import numpy as np, torch
 import armadillocudalinearinterpolation_b200 as B
 n = 4096
