@@ -286,3 +286,25 @@ def test_interp2_tile_layout_same_bits(b200, oracle, dt, shape):
     xq[1000:1000 + y.size] = x[-1]; yq[1000:1000 + y.size] = y   # every y knot on the last column
     for extrap in (np.nan, -1.5):
         assert same_bits(plan.scattered(xq, yq, extrap=extrap), oracle.interp2_scattered(x, y, z, xq, yq, extrap=extrap, nthreads=8))
+
+
+def test_affine_detection_is_exact(b200, oracle):
+    """One knot moved by one ulp makes an axis non-affine (the plan-time check is knot by knot, bit by bit):
+    the table path must then be taken and give the oracle's bits; so must the affine path on the clean axis."""
+    rng = np.random.default_rng(21)
+    for n in (1000, 8000):                       # shared-memory interp1 path / also large enough for tiles etc.
+        x = np.linspace(-1.0, 1.0, n); xp = x.copy(); xp[n // 3] = np.nextafter(xp[n // 3], 2.0)
+        y = rng.standard_normal(n)
+        xi = rng.uniform(-1.05, 1.05, 300_001); xi[:4] = [x[0], x[-1], xp[n // 3], x[n // 3]]
+        for knots in (x, xp):
+            yi, idx = b200.Interp1Plan(knots, y)(xi, extrap=0.5, return_index=True)
+            yo, io = oracle.interp1(knots, y, xi, extrap=0.5, nthreads=8)
+            assert same_bits(yi, yo) and np.array_equal(idx, io)
+    x = np.linspace(0.0, 3.0, 257); xp = x.copy(); xp[5] = np.nextafter(xp[5], 0.0)
+    yk = np.linspace(-1.0, 0.0, 129)
+    z = rng.standard_normal((129, 257))
+    xq = rng.uniform(-0.1, 3.1, 200_000); yq = rng.uniform(-1.1, 0.1, 200_000)
+    for knots in (x, xp):
+        for flags in (0, b200.Interp2Plan.FORCE_TILES, b200.Interp2Plan.NO_CELLS | b200.Interp2Plan.NO_TILES):
+            got = b200.Interp2Plan(knots, yk, z, flags=flags).scattered(xq, yq, extrap=9.0)
+            assert same_bits(got, oracle.interp2_scattered(knots, yk, z, xq, yq, extrap=9.0, nthreads=8))
