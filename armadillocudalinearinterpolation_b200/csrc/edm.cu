@@ -31,8 +31,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <new>
 #include <vector>
+#include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include "b200_edm.h"
 #include "common.cuh"
 
@@ -819,6 +822,29 @@ __global__ void convert_kernel(const T* __restrict__ in, U* __restrict__ out, si
   if (i < n) out[i] = (U)in[i];
 }
 
+// ---------------------------------------------------------------- finite differences ----
+// The callers' column loop (NewtonSolver.cpp:181-195, Stability.cpp:95-109) formed on the device:
+// local column k < ncols_pert is u + eps e_{col_begin+k} (one rounded add, as `du(i) += epsilon`),
+// the last local column is u itself (the base evaluation every device repeats).
+__global__ void edm_fd_columns_kernel(const double* __restrict__ u, unsigned n, double eps, unsigned col_begin,
+                                      unsigned ncols_pert, double* __restrict__ z) {
+  const size_t total = (size_t)(ncols_pert + 1) * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned k = (unsigned)(i / n), r = (unsigned)(i % n);
+    double v = u[r];
+    if (k < ncols_pert && r == col_begin + k) v = __dadd_rn(v, eps);
+    z[i] = v;
+  }
+}
+// jacobian.col(i) = (df - f) * pow(epsilon,-1)  (NewtonSolver.cpp:194, Stability.cpp:108); f = local column ncols_pert
+__global__ void edm_fd_jacobian_kernel(const double* __restrict__ f, unsigned n, unsigned ncols_pert, double inv_eps,
+                                       double* __restrict__ jac) {
+  const size_t total = (size_t)ncols_pert * n;
+  const double* f0 = f + (size_t)ncols_pert * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    jac[i] = __dmul_rn(__dsub_rn(f[i], f0[i % n]), inv_eps);
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -836,6 +862,18 @@ struct b200_edm {
   uint32_t profile_nc = 0;   // 0: front map; > 0: profile map on this many coarse knots
   // in-process multi-GPU: helper handles on other devices of this process (b200_edm_set_devices)
   std::vector<b200_edm*> helpers;
+  std::vector<int> devs;             // devs[0] = this handle's device, then the helpers'
+  std::vector<ncclComm_t> comms;     // one communicator per device (ncclCommInitAll); empty: peer copies
+  void* d_gather = nullptr;          // all-gather buffer (every device holds the full result)
+  size_t gather_cap = 0;
+  int32_t* d_gather_acc = nullptr;
+  size_t gather_acc_cap = 0;
+  double* d_u = nullptr;             // base vector of a finite-difference Jacobian
+  size_t u_cap = 0;
+  double* d_jac = nullptr;           // item-sharded Jacobian: difference quotients formed on the primary
+  size_t jac_cap = 0;
+  bool last_sliced = false;          // the last evaluation left only a slice of the per-item arrays here
+  bool last_pos_external = false;
   cudaEvent_t ev_helper = nullptr;
   void* d_uc = nullptr;      // profile map: columns converted to the run's arithmetic type
   int device = 0;
@@ -1135,68 +1173,247 @@ void sync_helper(const b200_edm* h, b200_edm* g) {
   g->debug = 0; g->timing = 0;
 }
 
-// In-process multi-GPU: the (column, realisation) items are split over the primary device and the
-// helpers; every device lifts all columns (cheap) and evolves its slice on its own stream; the
-// helpers' positions / accept flags are copied peer-to-peer into the primary's item-ordered arrays,
-// where the usual fixed-order reduction runs — bitwise the single-device result.
-template <typename T>
-int evolve_multi(b200_edm* h, const double* z_cols, size_t n, size_t ncols, cudaStream_t st) {
-  const size_t nitems = ncols * h->R, ndev = h->helpers.size() + 1, nd = ndim(h), es = esize(h);
-  const size_t per = (nitems + ndev - 1) / ndev;
-  // helpers first (they run while the primary works on its own slice)
-  for (size_t d = 1; d < ndev; ++d) {
-    b200_edm* g = h->helpers[d - 1];
-    const size_t lo = d * per < nitems ? d * per : nitems, hi = (d + 1) * per < nitems ? (d + 1) * per : nitems;
-    if (hi <= lo) continue;
-    sync_helper(h, g);
-    B200_CUDA(cudaSetDevice(g->device));
-    B200_TRY(ensure_batch(g, ncols, hi - lo));
-    B200_TRY(ensure_ensemble<T>(g, g->stream));
-    B200_TRY(upload_z(g, z_cols, n, ncols, g->stream));
-    B200_TRY(run_prepare<T>(g, ncols, g->stream));
-    B200_TRY(run_evolve<T>(g, lo, hi, (T*)g->d_pos, g->d_accept, g->stream));
-    B200_CUDA(cudaMemcpyPeerAsync((char*)h->d_pos + lo * nd * es, h->device, g->d_pos, g->device, (hi - lo) * nd * es, g->stream));
-    B200_CUDA(cudaMemcpyPeerAsync(h->d_accept + lo, h->device, g->d_accept, g->device, (hi - lo) * sizeof(int32_t), g->stream));
-    B200_CUDA(cudaEventRecord(g->ev_done, g->stream));
+// ---- NCCL, loaded on first use (the library has no link-time dependency on it) ----
+struct NcclApi {
+  void* so = nullptr;
+  decltype(&ncclCommInitAll) comm_init_all = nullptr;
+  decltype(&ncclCommDestroy) comm_destroy = nullptr;
+  decltype(&ncclAllGather) all_gather = nullptr;
+  decltype(&ncclGroupStart) group_start = nullptr;
+  decltype(&ncclGroupEnd) group_end = nullptr;
+  decltype(&ncclGetErrorString) error_string = nullptr;
+  bool tried = false, ok = false;
+};
+NcclApi g_nccl;
+bool load_nccl() {
+  NcclApi& a = g_nccl;
+  if (a.tried) return a.ok;
+  a.tried = true;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    a.so = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (a.so) break;
   }
-  B200_CUDA(cudaSetDevice(h->device));
-  const size_t hi0 = per < nitems ? per : nitems;
-  B200_TRY(run_evolve<T>(h, 0, hi0, (T*)h->d_pos, h->d_accept, st));
-  for (size_t d = 1; d < ndev; ++d) {
-    const size_t lo = d * per < nitems ? d * per : nitems, hi = (d + 1) * per < nitems ? (d + 1) * per : nitems;
-    if (hi > lo) B200_CUDA(cudaStreamWaitEvent(st, h->helpers[d - 1]->ev_done, 0));
+  if (!a.so) return false;
+#define B200_SYM(field, sym) a.field = (decltype(a.field))dlsym(a.so, #sym); if (!a.field) return false
+  B200_SYM(comm_init_all, ncclCommInitAll);
+  B200_SYM(comm_destroy, ncclCommDestroy);
+  B200_SYM(all_gather, ncclAllGather);
+  B200_SYM(group_start, ncclGroupStart);
+  B200_SYM(group_end, ncclGroupEnd);
+  B200_SYM(error_string, ncclGetErrorString);
+#undef B200_SYM
+  return a.ok = true;
+}
+#define B200_NCCL(call)                                                                            \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != ncclSuccess) return fail(B200_ERR_CUDA, "NCCL error %d (%s) in %s", (int)r__, g_nccl.error_string(r__), #call); \
+  } while (0)
+
+b200_edm* dev_handle(b200_edm* h, size_t d) { return d == 0 ? h : h->helpers[d - 1]; }
+
+int ensure_gather(b200_edm* g, size_t bytes, size_t acc_items) {
+  if (bytes > g->gather_cap) {
+    cudaFree(g->d_gather); g->d_gather = nullptr; g->gather_cap = 0;
+    B200_CUDA(cudaMalloc(&g->d_gather, bytes));
+    g->gather_cap = bytes;
+  }
+  if (acc_items > g->gather_acc_cap) {
+    cudaFree(g->d_gather_acc); g->d_gather_acc = nullptr; g->gather_acc_cap = 0;
+    B200_CUDA(cudaMalloc(&g->d_gather_acc, acc_items * sizeof(int32_t)));
+    g->gather_acc_cap = acc_items;
+  }
+  return B200_OK;
+}
+int ensure_u(b200_edm* g, size_t n) {
+  if (n > g->u_cap) {
+    cudaFree(g->d_u); g->d_u = nullptr; g->u_cap = 0;
+    B200_CUDA(cudaMalloc(&g->d_u, n * sizeof(double)));
+    g->u_cap = n;
   }
   return B200_OK;
 }
 
+// every device holds `slot_bytes` of results at slot d of its gather buffer: exchange them so that every
+// device (in particular the primary) holds all slots.  One in-place ncclAllGather per device inside one
+// group (single process driving several devices); without communicators (B200_EDM_NO_NCCL=1) the
+// helpers' slots are peer-copied to the primary instead.
+int exchange_slots(b200_edm* h, cudaStream_t st, size_t slot_bytes, size_t acc_slot_items) {
+  const size_t ndev = h->helpers.size() + 1;
+  if (!h->comms.empty()) {
+    nvtxRangePushA("edm:nccl_all_gather");
+    B200_NCCL(g_nccl.group_start());
+    for (size_t d = 0; d < ndev; ++d) {
+      b200_edm* g = dev_handle(h, d);
+      cudaStream_t gs = d == 0 ? st : g->stream;
+      if (slot_bytes)
+        B200_NCCL(g_nccl.all_gather((const char*)g->d_gather + d * slot_bytes, g->d_gather, slot_bytes, ncclChar, h->comms[d], gs));
+      if (acc_slot_items)
+        B200_NCCL(g_nccl.all_gather(g->d_gather_acc + d * acc_slot_items, g->d_gather_acc, acc_slot_items, ncclInt32, h->comms[d], gs));
+    }
+    B200_NCCL(g_nccl.group_end());
+    nvtxRangePop();
+    return B200_OK;
+  }
+  for (size_t d = 1; d < ndev; ++d) {
+    b200_edm* g = dev_handle(h, d);
+    B200_CUDA(cudaSetDevice(g->device));
+    if (slot_bytes)
+      B200_CUDA(cudaMemcpyPeerAsync((char*)h->d_gather + d * slot_bytes, h->device, (const char*)g->d_gather + d * slot_bytes,
+                                    g->device, slot_bytes, g->stream));
+    if (acc_slot_items)
+      B200_CUDA(cudaMemcpyPeerAsync(h->d_gather_acc + d * acc_slot_items, h->device, g->d_gather_acc + d * acc_slot_items,
+                                    g->device, acc_slot_items * sizeof(int32_t), g->stream));
+    B200_CUDA(cudaEventRecord(g->ev_done, g->stream));
+  }
+  B200_CUDA(cudaSetDevice(h->device));
+  for (size_t d = 1; d < ndev; ++d) B200_CUDA(cudaStreamWaitEvent(st, h->helpers[d - 1]->ev_done, 0));
+  return B200_OK;
+}
+
+// One batch of evaluations over all devices of the handle (1 = just this one).
+//   fd == false: z_or_u = n x ncols host columns; result = F of every column.
+//   fd == true : z_or_u = u (n entries); the ncols = n perturbed columns u + eps e_i are formed on the
+//                device; result = the Jacobian columns (F(u + eps e_i) - F(u)) / eps and F(u).
+// Sharding: with many columns every device owns a contiguous block of WHOLE columns
+// (lift, evolve, fixed-order reduction and, for fd, the difference quotient all local; the base column is
+// evaluated redundantly on every device) and only the n-vectors per column are all-gathered.  With few
+// columns (the reference's n = 3) the (column, realisation) work items are split instead, positions and
+// accept flags are all-gathered and the primary reduces.  Either way the result is bitwise that of one device.
 template <typename T>
-int compute_batch(b200_edm* h, const double* z_cols, size_t n, size_t ncols, double* f_out) {
+int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, bool fd, double eps, double* out_cols,
+                  double* f0_out) {
   B200_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  const size_t nitems = ncols * h->R;
+  const size_t ndev = h->helpers.size() + 1, R = h->R, nd = ndim(h), es = esize(h);
+  if (n != nd)
+    return fail(B200_ERR_INVALID_ARG, "vector length %zu != %s %zu", n, h->profile_nc ? "2 x coarse knots" : "no_fronts", nd);
   B200_TRY(order_after_previous(h, st));
-  B200_TRY(ensure_batch(h, ncols, nitems));
-  B200_TRY(ensure_ensemble<T>(h, st));
-  B200_TRY(upload_z(h, z_cols, n, ncols, st));
-  B200_TRY(run_prepare<T>(h, ncols, st));
-  if (!h->helpers.empty()) B200_TRY(evolve_multi<T>(h, z_cols, n, ncols, st));
-  else B200_TRY(run_evolve<T>(h, 0, nitems, (T*)h->d_pos, h->d_accept, st));
-  B200_TRY(run_reduce<T>(h, ncols, (const T*)h->d_pos, h->d_accept, h->d_f, st));
-  double* h_f = h->h_pin + n * ncols;
-  B200_CUDA(cudaMemcpyAsync(h_f, h->d_f, n * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (h->up_pending) { B200_CUDA(cudaEventSynchronize(h->ev_up)); h->up_pending = false; }
+  B200_TRY(ensure_pinned(h, 2 * n * (ncols + 1)));     // z / u in, results out (never re-allocated below)
+  const bool by_columns = ndev == 1 || ncols >= 4 * ndev;
+  const size_t cpd = by_columns ? (ncols + ndev - 1) / ndev : ncols;          // result columns per device slot
+  const size_t nitems_all = (ncols + (fd ? 1 : 0)) * R;
+  const size_t per = (nitems_all + ndev - 1) / ndev;                            // item mode: items per device
+  h->last_sliced = ndev > 1;
+  h->last_pos_external = false;
+
+  for (size_t dd = 0; dd < ndev; ++dd) {
+    const size_t d = ndev - 1 - dd;            // helpers first: they run while the primary is being fed
+    b200_edm* g = dev_handle(h, d);
+    cudaStream_t gs = d == 0 ? st : g->stream;
+    if (d) sync_helper(h, g);
+    B200_CUDA(cudaSetDevice(g->device));
+    // local column set
+    size_t c_lo = 0, c_hi = ncols;
+    if (by_columns) { c_lo = d * cpd < ncols ? d * cpd : ncols; c_hi = (d + 1) * cpd < ncols ? (d + 1) * cpd : ncols; }
+    const size_t cols_res = c_hi - c_lo;                       // result columns computed here
+    const size_t cols_loc = cols_res + (fd ? 1 : 0);           // + the base column
+    size_t i_lo = 0, i_hi = cols_loc * R;
+    if (!by_columns) { i_lo = d * per < nitems_all ? d * per : nitems_all; i_hi = (d + 1) * per < nitems_all ? (d + 1) * per : nitems_all; }
+    B200_TRY(ensure_batch(g, cols_loc > cpd + 1 ? cols_loc : cpd + 1, (i_hi - i_lo) ? (i_hi - i_lo) : 1));
+    B200_TRY(ensure_ensemble<T>(g, gs));
+    if (by_columns) B200_TRY(ensure_gather(g, ndev * cpd * nd * sizeof(double), 0));
+    else B200_TRY(ensure_gather(g, ndev * per * nd * es, ndev * per));
+    if (cols_res == 0 && by_columns) continue;                 // more devices than columns: idle, still joins the gather
+    nvtxRangePushA("edm:lift");
+    if (fd) {
+      B200_TRY(ensure_u(g, n));
+      if (g->up_pending) { B200_CUDA(cudaEventSynchronize(g->ev_up)); g->up_pending = false; }
+      B200_TRY(ensure_pinned(g, 2 * n));
+      memcpy(g->h_pin, z_or_u, n * sizeof(double));
+      B200_CUDA(cudaMemcpyAsync(g->d_u, g->h_pin, n * sizeof(double), cudaMemcpyHostToDevice, gs));
+      B200_CUDA(cudaEventRecord(g->ev_up, gs));
+      g->up_pending = true;
+      const size_t total = cols_loc * n;
+      edm_fd_columns_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, gs>>>(
+          g->d_u, (unsigned)n, eps, (unsigned)c_lo, (unsigned)cols_res, g->d_z);
+      B200_CUDA(cudaGetLastError());
+    } else {
+      B200_TRY(upload_z(g, z_or_u + c_lo * n, n, cols_loc, gs));
+    }
+    B200_TRY(run_prepare<T>(g, cols_loc, gs));
+    nvtxRangePop();
+    nvtxRangePushA("edm:evolve");
+    if (by_columns) {
+      B200_TRY(run_evolve<T>(g, 0, cols_loc * R, (T*)g->d_pos, g->d_accept, gs));
+    } else {
+      B200_TRY(run_evolve<T>(g, i_lo, i_hi, (T*)((char*)g->d_gather + d * per * nd * es), g->d_gather_acc + d * per, gs));
+    }
+    nvtxRangePop();
+    if (by_columns) {
+      nvtxRangePushA("edm:reduce");
+      double* slot = (double*)g->d_gather + d * cpd * nd;
+      if (fd) {
+        B200_TRY(run_reduce<T>(g, cols_loc, (const T*)g->d_pos, g->d_accept, g->d_f, gs));
+        const size_t total = cols_res * n;
+        edm_fd_jacobian_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, gs>>>(
+            g->d_f, (unsigned)n, (unsigned)cols_res, pow(eps, -1), slot);
+        B200_CUDA(cudaGetLastError());
+      } else {
+        B200_TRY(run_reduce<T>(g, cols_loc, (const T*)g->d_pos, g->d_accept, slot, gs));
+      }
+      nvtxRangePop();
+    }
+  }
+  B200_CUDA(cudaSetDevice(h->device));
+  if (ndev > 1) {
+    if (by_columns) B200_TRY(exchange_slots(h, st, cpd * nd * sizeof(double), 0));
+    else B200_TRY(exchange_slots(h, st, per * nd * es, per));
+    B200_CUDA(cudaSetDevice(h->device));
+  }
+  const double* d_result = (const double*)h->d_gather;
+  const double* d_f0 = nullptr;
+  if (by_columns) {
+    if (fd) d_f0 = h->d_f + (((cpd < ncols ? cpd : ncols)) * n);     // the primary's base column (local column cols_res)
+  } else {
+    // item mode: all positions are here in item order; the usual fixed-order reduction over every column
+    nvtxRangePushA("edm:reduce");
+    B200_TRY(run_reduce<T>(h, ncols + (fd ? 1 : 0), (const T*)h->d_gather, h->d_gather_acc, h->d_f, st));
+    if (fd) {
+      const size_t total = ncols * n;
+      if (total > h->jac_cap) {
+        cudaFree(h->d_jac); h->d_jac = nullptr; h->jac_cap = 0;
+        B200_CUDA(cudaMalloc(&h->d_jac, total * sizeof(double)));
+        h->jac_cap = total;
+      }
+      edm_fd_jacobian_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, st>>>(
+          h->d_f, (unsigned)n, (unsigned)ncols, pow(eps, -1), h->d_jac);
+      B200_CUDA(cudaGetLastError());
+      d_result = h->d_jac;
+      d_f0 = h->d_f + ncols * n;
+    } else {
+      d_result = h->d_f;
+    }
+    nvtxRangePop();
+  }
+  double* h_res = h->h_pin + n * (ncols + 1);
+  B200_CUDA(cudaMemcpyAsync(h_res, d_result, n * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (d_f0) B200_CUDA(cudaMemcpyAsync(h->h_pin, d_f0, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaMemcpyAsync(&h->last_clamped, h->d_clamped, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (h->debug || h->timing)
     B200_CUDA(cudaMemcpyAsync(h->last_counters, h->d_counters, sizeof(h->last_counters), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
+  for (size_t d = 1; d < ndev; ++d) {   // helpers have nothing left in flight that the caller's next call could race with
+    B200_CUDA(cudaSetDevice(h->helpers[d - 1]->device));
+    B200_CUDA(cudaStreamSynchronize(h->helpers[d - 1]->stream));
+  }
+  B200_CUDA(cudaSetDevice(h->device));
   h->done_pending = false;
-  memcpy(f_out, h_f, n * ncols * sizeof(double));
-  h->last_cols = ncols;
+  memcpy(out_cols, h_res, n * ncols * sizeof(double));
+  if (f0_out && d_f0) memcpy(f0_out, h->h_pin, n * sizeof(double));
+  h->last_cols = by_columns ? (cpd < ncols ? cpd : ncols) + (fd ? 1 : 0) : ncols + (fd ? 1 : 0);
   if (h->timing) {
     float ms = 0.f;
     B200_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
   }
   return B200_OK;
+}
+
+template <typename T>
+int compute_batch(b200_edm* h, const double* z_cols, size_t n, size_t ncols, double* f_out) {
+  return compute_multi<T>(h, z_cols, n, ncols, false, 0.0, f_out, nullptr);
 }
 
 }  // namespace
@@ -1239,9 +1456,12 @@ int b200_edm_destroy(b200_edm* h) {
   if (!h) return B200_OK;
   for (b200_edm* g : h->helpers) b200_edm_destroy(g);
   h->helpers.clear();
+  if (!h->comms.empty() && g_nccl.ok) for (ncclComm_t c : h->comms) g_nccl.comm_destroy(c);
+  h->comms.clear();
   cudaSetDevice(h->device);
   free_ensemble(h);
   free_batch(h);
+  cudaFree(h->d_gather); cudaFree(h->d_gather_acc); cudaFree(h->d_u); cudaFree(h->d_jac);
   cudaFree(h->d_clamped); cudaFree(h->d_counters);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1289,7 +1509,10 @@ int b200_edm_set_no_neurons(b200_edm* h, uint32_t N) {
 int b200_edm_set_param_stddev(b200_edm* h, double sigma) {
   B200_TRY(check_handle(h, "edm_set_param_stddev"));
   if (!(sigma >= 0)) return fail(B200_ERR_INVALID_ARG, "sigma must be >= 0 (EventDrivenMap.cu:319)");
-  if (sigma != h->sigma) { h->sigma = sigma; h->beta_dirty = true; }
+  if (sigma != h->sigma) {
+    h->sigma = sigma; h->beta_dirty = true;
+    if (sigma == 0.0) { cudaSetDevice(h->device); cudaFree(h->beta); h->beta = nullptr; }   // no stale ensemble behind DBG_BETA
+  }
   return B200_OK;
 }
 int b200_edm_set_parameter(b200_edm* h, uint32_t par_id, double value) {
@@ -1332,6 +1555,9 @@ int b200_edm_set_devices(b200_edm* h, const int* device_ids, size_t ndevices) {
   }
   for (b200_edm* g : h->helpers) b200_edm_destroy(g);
   h->helpers.clear();
+  if (!h->comms.empty() && g_nccl.ok) for (ncclComm_t c : h->comms) g_nccl.comm_destroy(c);
+  h->comms.clear();
+  h->devs.assign(device_ids, device_ids + ndevices);
   int rc = B200_OK;
   for (size_t i = 1; i < ndevices && rc == B200_OK; ++i) {
     rc = cudaSetDevice(device_ids[i]) == cudaSuccess ? B200_OK : fail(B200_ERR_CUDA, "cudaSetDevice(%d) failed", device_ids[i]);
@@ -1347,7 +1573,22 @@ int b200_edm_set_devices(b200_edm* h, const int* device_ids, size_t ndevices) {
     }
   }
   cudaSetDevice(h->device);
-  if (rc != B200_OK) { for (b200_edm* g : h->helpers) b200_edm_destroy(g); h->helpers.clear(); }
+  // the exchange is one NCCL all-gather per evaluation batch (north-star); B200_EDM_NO_NCCL=1 keeps
+  // the round-1 peer-copy exchange for A/B timing
+  const char* no_nccl = getenv("B200_EDM_NO_NCCL");
+  if (rc == B200_OK && ndevices > 1 && !(no_nccl && no_nccl[0] == '1')) {
+    if (!load_nccl()) rc = fail(B200_ERR_UNSUPPORTED, "edm_set_devices: libnccl.so.2 could not be loaded (%s)", dlerror());
+    if (rc == B200_OK) {
+      h->comms.resize(ndevices);
+      ncclResult_t r = g_nccl.comm_init_all(h->comms.data(), (int)ndevices, h->devs.data());
+      if (r != ncclSuccess) {
+        h->comms.clear();
+        rc = fail(B200_ERR_CUDA, "edm_set_devices: ncclCommInitAll over %zu devices failed: %s", ndevices, g_nccl.error_string(r));
+      }
+    }
+    cudaSetDevice(h->device);
+  }
+  if (rc != B200_OK) { for (b200_edm* g : h->helpers) b200_edm_destroy(g); h->helpers.clear(); h->devs.resize(1); }
   return rc;
 }
 
@@ -1382,18 +1623,12 @@ int b200_edm_compute_dfdu(b200_edm* h, const double* u, size_t n, double eps, do
   if (!u || !jac_out) return fail(B200_ERR_INVALID_ARG, "edm_compute_dfdu: NULL argument");
   if (n != ndim(h)) return fail(B200_ERR_INVALID_ARG, "vector length %zu != problem dimension %zu", n, ndim(h));
   if (!(eps != 0.0)) return fail(B200_ERR_INVALID_ARG, "finite-difference epsilon must be non-zero");
-  // columns 0..n-1: u + eps e_i (NewtonSolver.cpp:184-188), column n: u
-  std::vector<double> zc((n + 1) * n), fc((n + 1) * n);
-  for (size_t c = 0; c <= n; ++c) {
-    for (size_t r = 0; r < n; ++r) zc[c * n + r] = u[r];
-    if (c < n) zc[c * n + c] += eps;
-  }
-  B200_TRY(b200_edm_compute_f_batch(h, zc.data(), n, n + 1, fc.data()));
-  const double inv = pow(eps, -1);  // NewtonSolver.cpp:194
-  for (size_t c = 0; c < n; ++c)
-    for (size_t r = 0; r < n; ++r) jac_out[c * n + r] = (fc[c * n + r] - fc[n * n + r]) * inv;
-  if (f0_out) memcpy(f0_out, &fc[n * n], n * sizeof(double));
-  return B200_OK;
+  if (!h->profile_nc && (!(u[0] == u[0]) || u[0] == 0.0 || u[0] + eps == 0.0))
+    return fail(B200_ERR_INVALID_ARG, "wave speed u[0] (and u[0] + eps) must be finite and non-zero");
+  // columns u + eps e_i (NewtonSolver.cpp:184-188) and the base column u are formed on the device(s);
+  // the difference quotients (NewtonSolver.cpp:194) too, next to the columns they belong to
+  return h->prec == B200_F64 ? compute_multi<double>(h, u, n, n, true, eps, jac_out, f0_out)
+                             : compute_multi<float>(h, u, n, n, true, eps, jac_out, f0_out);
 }
 
 int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_t ncols,
@@ -1423,6 +1658,8 @@ int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     B200_CUDA(cudaGetLastError());
   }
   h->last_cols = ncols;
+  h->last_sliced = !(item_begin == 0 && item_end == ncols * h->R);
+  h->last_pos_external = (h->prec == B200_F64);   // positions went to the caller's buffer, not d_pos
   return mark_done(h, st);
 }
 
@@ -1501,6 +1738,13 @@ int b200_edm_debug_fetch(b200_edm* h, b200_edm_debug_what what, void* out, size_
       what != B200_EDM_DBG_POSITION && what != B200_EDM_DBG_EVENT_COUNT && what != B200_EDM_DBG_BETA &&
       what != B200_EDM_DBG_COUPLING)
     return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: array %d does not exist for the profile map", (int)what);
+  if (h->last_sliced && (what == B200_EDM_DBG_LAST_INDEX || what == B200_EDM_DBG_LAST_TIME || what == B200_EDM_DBG_CROSSED_INDEX ||
+                         what == B200_EDM_DBG_CROSSED_TIME || what == B200_EDM_DBG_ACCEPT || what == B200_EDM_DBG_POSITION ||
+                         what == B200_EDM_DBG_EVENT_COUNT))
+    return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: the last evaluation was sharded (item slice / several devices); "
+                                      "per-item arrays are not all on this handle");
+  if (h->last_pos_external && what == B200_EDM_DBG_POSITION)
+    return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: the last evaluation wrote its positions to the caller's device buffer");
   const void* src = nullptr;
   size_t count = 0;
   bool real = false, is_int = false;

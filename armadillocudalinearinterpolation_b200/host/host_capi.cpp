@@ -1,5 +1,6 @@
 // host_capi.cpp — a few C entry points over the C++ host layer so that the test-suite (pytest,
 // ctypes) can drive NewtonSolver / Stability / EventDrivenMapB200 exactly as a C++ user would.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <sstream>
@@ -147,6 +148,104 @@ int b200_host_edm_stability(double beta, unsigned R, unsigned N, const double* u
     arma::cx_vec w = st.ComputeEigenvalues(u);
     for (int i = 0; i < n; ++i) { eig_re[i] = w(i).real(); eig_im[i] = w(i).imag(); }
     return st.ComputeNumUnstableEigenvalues(u);
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+
+// ---- BASELINE config 4: NewtonSolver with the reference driver's settings (Driver.cu:28-37,71) on the drop-in
+// map spread over `ndev` devices of this process (EventDrivenMapB200::SetDevices -> NCCL all-gather inside the
+// C-ABI).  mode as above.  ms_out[0] = wall time of Solve(), ms_out[1] = of one extra ComputeDFDU at the solution.
+int b200_host_edm_newton_multi(double beta, unsigned R, unsigned N, const double* guess, int n, double tol, int max_it,
+                               double eps, int mode, double sigma, int ndev, const int* devs, double* solution,
+                               double* history, int* n_history, double* jac_out, double* ms_out) {
+  try {
+    arma::vec p(1);
+    p(0) = beta;
+    EventDrivenMapB200 map(&p, R, N, (unsigned)n);
+    map.SetPrintOutput(false);
+    map.SetFiniteDifferenceEpsilon(eps);
+    if (sigma > 0) map.SetParameterStdDev((float)sigma);
+    if (ndev > 1) map.SetDevices(devs, (unsigned)ndev);
+    arma::vec g(n), sol(n), hist;
+    for (int i = 0; i < n; ++i) g(i) = guess[i];
+    NewtonSolver::ParameterList pars;
+    pars.tolerance = tol; pars.maxIterations = max_it; pars.printOutput = false; pars.damping = 1.0;
+    NewtonSolver* solver = mode ? new NewtonSolver(&map, &map, &g, &pars) : new NewtonSolver(&map, &g, &pars);
+    pars.finiteDifferenceEpsilon = eps;      // set after construction, as Driver.cu:37
+    AbstractNonlinearSolver::ExitFlagType flag;
+    arma::mat J(n, n);
+    { arma::vec warm(n); map.ComputeF(g, warm); }          // context / allocations outside the timed region
+    auto t0 = std::chrono::steady_clock::now();
+    solver->Solve(sol, hist, flag, &J);
+    auto t1 = std::chrono::steady_clock::now();
+    arma::mat J2(n, n);
+    map.ComputeDFDU(sol, J2);
+    auto t2 = std::chrono::steady_clock::now();
+    delete solver;
+    if (ms_out) {
+      ms_out[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+      ms_out[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    }
+    for (int i = 0; i < n; ++i) solution[i] = sol(i);
+    *n_history = (int)hist.n_elem;
+    for (arma::uword i = 0; i < hist.n_elem; ++i) history[i] = hist(i);
+    if (jac_out) std::memcpy(jac_out, J.memptr(), sizeof(double) * n * n);
+    return flag == AbstractNonlinearSolver::ExitFlagType::converged ? 1 : 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// ---- BASELINE config 5: Stability::ComputeNumUnstableEigenvalues (Stability.cpp:22-36) of the profile map
+// (n = 2 n_coarse) through the C++ classes, Jacobian via the plug-in (Stability.cpp:59-62) over `ndev` devices,
+// eigenvalues via arma::eig_gen.  ms_out[0] = the whole call (Jacobian + eigenvalues), ms_out[1] = a Jacobian
+// alone, ms_out[2] = eig_gen alone on that Jacobian.  jac_out (n x n, nullable) receives the Jacobian.
+int b200_host_profile_stability(double beta, unsigned R, unsigned N, unsigned n_coarse, double T, const double* u_in,
+                                double eps, int ndev, const int* devs, double* ms_out, double* jac_out,
+                                double* eig_re, double* eig_im) {
+  try {
+    arma::vec p(1);
+    p(0) = beta;
+    const int n = 2 * (int)n_coarse;
+    EventDrivenMapB200 map(&p, R, N, 3);
+    map.SetPrintOutput(false);
+    map.SetTimeHorizon((float)T);
+    map.SetProfileMode(n_coarse);
+    map.SetFiniteDifferenceEpsilon(eps);
+    if (ndev > 1) map.SetDevices(devs, (unsigned)ndev);
+    arma::vec u(n);
+    for (int i = 0; i < n; ++i) u(i) = u_in[i];
+    Stability st(Stability::ProblemType::equationFree, &map, &map);
+    arma::mat J(n, n);
+    map.ComputeDFDU(u, J);                                  // warm-up: allocations, NCCL channels
+    auto t0 = std::chrono::steady_clock::now();
+    const int unstable = st.ComputeNumUnstableEigenvalues(u);
+    auto t1 = std::chrono::steady_clock::now();
+    map.ComputeDFDU(u, J);
+    auto t2 = std::chrono::steady_clock::now();
+    arma::mat JI = J + arma::mat(n, n, arma::fill::eye);    // Stability.cpp:68-71
+    arma::cx_vec w = arma::eig_gen(JI);
+    auto t3 = std::chrono::steady_clock::now();
+    if (ms_out) {
+      ms_out[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+      ms_out[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+      ms_out[2] = std::chrono::duration<double, std::milli>(t3 - t2).count();
+    }
+    if (jac_out) std::memcpy(jac_out, J.memptr(), sizeof(double) * n * n);
+    if (eig_re) for (int i = 0; i < n; ++i) { eig_re[i] = w(i).real(); eig_im[i] = w(i).imag(); }
+    return unstable;
+  } catch (const std::exception& e) { g_err = e.what(); return -1000; }
+}
+
+// arma::eig_gen as the host layer sees it (cuSOLVER behind the shim for n >= 128, own QR below / on request)
+int b200_host_eig_gen(int n, const double* A_colmajor, double* eig_re, double* eig_im, double* ms_out) {
+  try {
+    arma::mat A(n, n);
+    std::memcpy(A.memptr(), A_colmajor, sizeof(double) * n * n);
+    auto t0 = std::chrono::steady_clock::now();
+    arma::cx_vec w = arma::eig_gen(A);
+    auto t1 = std::chrono::steady_clock::now();
+    if (ms_out) *ms_out = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    for (int i = 0; i < n; ++i) { eig_re[i] = w(i).real(); eig_im[i] = w(i).imag(); }
+    return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 

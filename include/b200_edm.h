@@ -109,10 +109,23 @@ int b200_edm_compute_dfdu(b200_edm* h, const double* u, size_t n, double eps,
 int b200_edm_set_profile_mode(b200_edm* h, uint32_t n_coarse);
 
 /* ---- in-process multi-GPU (for C++ callers without a launcher) ----
- * After this call compute_f / compute_f_batch / compute_dfdu split their (column, realisation) work
- * items over the listed devices of THIS process (device_ids[0] must be the handle's device); results
- * are bitwise those of a single device.  The reference is single-GPU (EventDrivenMap.cu:182,196). */
+ * After this call compute_f / compute_f_batch / compute_dfdu shard over the listed devices of THIS process
+ * (device_ids[0] must be the handle's device), so the reference's own callers — the finite-difference loops of
+ * NewtonSolver.cpp:91-94,181-195 and Stability.cpp:59-62,95-109 — scale without change:
+ *   - many columns (>= 4 per device, e.g. the 1001 evaluations of a 1000-dim Jacobian): every device owns a block
+ *     of WHOLE columns — perturbed columns formed on the device, lift, evolve, fixed-order mean, difference
+ *     quotient all local — and ONE ncclAllGather (single process, ncclCommInitAll) moves the n-vector of each
+ *     column to every device; the base column F(u) is evaluated redundantly instead of being broadcast;
+ *   - few columns (the reference's n = 3): the (column, realisation) work items are split, positions + accept
+ *     flags are all-gathered and the primary reduces.
+ * Results are bitwise those of a single device.  NCCL is loaded on first use; B200_EDM_NO_NCCL=1 exchanges with
+ * peer copies instead.  The reference is single-GPU (EventDrivenMap.cu:182,196). */
 int b200_edm_set_devices(b200_edm* h, const int* device_ids, size_t ndevices);
+
+/* Eigenvalues of a real general n x n matrix (column-major), the call behind arma::eig_gen in
+ * Stability::ComputeEigenvalues / ComputeNumUnstableEigenvalues (Stability.cpp:40,72): cuSOLVER's 64-bit GEEV
+ * on the current device (loaded on first use).  w_re / w_im receive the n eigenvalues. */
+int b200_eig_gen_f64(size_t n, const double* a_colmajor, double* w_re, double* w_im);
 
 /* ---- sharded evaluation (one process per GPU) ----
  * Work item id = col * no_realisations + r.  evolve_items runs items [item_begin,

@@ -131,42 +131,94 @@ def test_interp2_device_buffers(b200, oracle):
     assert same_bits(zi.cpu().numpy(), oracle.interp2_grid(x, y, z, xq[:100], yq[:64]))
 
 
-def test_full_size_properties_config1(b200):
-    """BASELINE config 1 at full size (1e6 knots, 1e7 queries): properties that need no oracle.
-    Interpolating the knots' own linear function reproduces it; brackets satisfy
-    X[a] <= xi < X[a+1]; knot hits return the knot value exactly."""
+def _config1_inputs(kind):
+    """BASELINE config 1 exactly as bench.py builds it (1e6 knots; SURVEY 8d seeds)."""
+    ng = 1_000_000
     rng = np.random.default_rng(1234)
-    ng, ni = 1_000_000, 10_000_000
-    xg = np.cumsum(0.5 + rng.random(ng)); xg = (xg - xg[0]) / (xg[-1] - xg[0])
-    yg = 3.0 * xg - 1.0
-    xi = rng.uniform(0.0, 1.0, ni)
+    xg = np.linspace(0.0, 1.0, ng) if kind == "uniform" else np.cumsum(0.5 + rng.random(ng))
+    xg = (xg - xg[0]) / (xg[-1] - xg[0])
+    yg = np.sin(2 * np.pi * xg) + 0.1 * np.random.default_rng(1235).standard_normal(ng)
+    return xg, yg
+
+
+@pytest.mark.parametrize("kind", ["uniform", "nonuniform"])
+@pytest.mark.parametrize("order", ["unsorted", "sorted"])
+def test_full_size_config1_bit_exact(b200, oracle, kind, order):
+    """BASELINE config 1 at its stated size — 1e6 knots x 1e7 queries, the bench's knots, values and
+    seeds — compared with the oracle on EVERY query: values bit for bit, bracket indices equal
+    (oracle = restatement of arma::interp1's interp1_helper_linear; parity with a real Armadillo
+    build is unpinned, Armadillo being absent from the image)."""
+    xg, yg = _config1_inputs(kind)
+    ni = 10_000_000
+    xi = np.random.default_rng(1236).uniform(xg[0], xg[-1], ni)
+    if order == "sorted":
+        xi.sort()
+    xi[:3] = [xg[0], xg[-1], xg[ni % xg.size]]
     plan = b200.Interp1Plan(xg, yg)
     yi, idx = plan(xi, return_index=True)
+    yo, io = oracle.interp1(xg, yg, xi, nthreads=os.cpu_count() or 8)
+    assert same_bits(yi, yo)
+    assert np.array_equal(idx, io)
+    # size-independent properties on top: brackets bracket, knot hits return the knot value
+    ng = xg.size
     assert idx.min() >= 0 and idx.max() <= ng - 1
     assert np.all(xg[idx] <= xi) and np.all(xi[idx < ng - 1] < xg[np.minimum(idx + 1, ng - 1)][idx < ng - 1])
-    assert np.max(np.abs(yi - (3.0 * xi - 1.0))) < 1e-14
     hits = plan(xg[::997], return_index=True)
     assert np.array_equal(hits[0], yg[::997]) and np.array_equal(hits[1], np.arange(ng)[::997])
 
 
-def test_full_size_properties_config2(b200):
-    """BASELINE config 2 at full size (4096^2 grid, 1e8 scattered queries, in chunks):
-    a bilinear function is reproduced; swapping axes of a transposed grid gives the same bits
-    up to the documented pass order (checked on a separable product, which is order-free)."""
+def test_full_size_config2_headline_plan_bit_exact(b200, oracle):
+    """BASELINE config 2 at its stated size through the HEADLINE plan of bench.py: the 4096^2 f64 grid of
+    seed 2234 with the default layout (overlapping 4x4 tiles, linspace axes recognised as affine) and all
+    1e8 queries of seed 2235 (torch's CUDA generator, as in the bench), every output compared bit for bit
+    with the oracle (restatement of arma::interp2 per point; Armadillo itself is absent, parity unpinned).
+    Also the host-buffer (e2e) path and a linear-reproduction property."""
     import torch
-    n = 4096
-    x = np.linspace(0.0, 1.0, n); y = np.linspace(0.0, 2.0, n)
-    z = (2.0 * x[None, :] - 0.5) * (0.25 * y[:, None] + 1.0)             # bilinear: exact up to rounding
+    import bench
+    x, y, z = bench.make_grid()
     plan = b200.Interp2Plan(x, y, z)
     g = torch.Generator(device="cuda").manual_seed(2235)
-    nq = 100_000_000
+    nq = bench.NQ
     xq = torch.rand(nq, generator=g, device="cuda", dtype=torch.float64)
-    yq = torch.rand(nq, generator=g, device="cuda", dtype=torch.float64) * 2.0
+    yq = torch.rand(nq, generator=g, device="cuda", dtype=torch.float64)
     zq = plan.scattered(xq, yq)
-    ref = (2.0 * xq - 0.5) * (0.25 * yq + 1.0)
-    err = (zq - ref).abs().max().item()
+    torch.cuda.synchronize()
+    hx, hy, hz = xq.cpu().numpy(), yq.cpu().numpy(), zq.cpu().numpy()
+    ref = oracle.interp2_scattered(x, y, z, hx, hy, nthreads=os.cpu_count() or 8)
+    assert same_bits(hz, ref)
+    # host-buffer C-ABI path (pageable numpy buffers): same bits on all 1e8 outputs
+    assert same_bits(plan.scattered(hx, hy), ref)
+    del ref, hz
+    # property at full size: a bilinear function is reproduced to rounding
+    zb = (2.0 * x[None, :] - 0.5) * (0.25 * y[:, None] + 1.0)
+    pb = b200.Interp2Plan(x, y, zb)
+    err = (pb.scattered(xq, yq) - (2.0 * xq - 0.5) * (0.25 * yq + 1.0)).abs().max().item()
     assert err < 5e-15
-    assert not torch.isnan(zq).any().item()
+
+
+def test_interp2_banded_then_grid_then_banded_one_plan(b200, oracle):
+    """Regression (round-1 advisor finding): the grid prologue used to free the banded pipeline's scratch
+    without resetting its capacity, so banded -> grid -> banded on ONE plan ran on freed memory."""
+    import torch
+    rng = np.random.default_rng(23)
+    x = np.unique(np.cumsum(0.5 + rng.random(513))); y = np.linspace(-2, 3, 384)
+    z = rng.standard_normal((y.size, x.size))
+    plan = b200.Interp2Plan(x, y, z, flags=b200.Interp2Plan.FORCE_CELLS | b200.Interp2Plan.FORCE_BANDS)
+    nq = 300_001
+    xq = rng.uniform(x[0], x[-1], nq); yq = rng.uniform(-2, 3, nq)
+    tx, ty = torch.from_numpy(xq).cuda(), torch.from_numpy(yq).cuda()
+    ref = oracle.interp2_scattered(x, y, z, xq, yq, nthreads=8)
+    z1 = plan.scattered(tx, ty); torch.cuda.synchronize()
+    assert same_bits(z1.cpu().numpy(), ref)
+    xi = np.sort(rng.uniform(x[0], x[-1], 700)); yi = np.sort(rng.uniform(-2, 3, 300))
+    assert same_bits(plan.grid(xi, yi), oracle.interp2_grid(x, y, z, xi, yi))       # first grid call: allocates
+    z2 = plan.scattered(tx, ty); torch.cuda.synchronize()
+    assert same_bits(z2.cpu().numpy(), ref)
+    xi2 = np.sort(rng.uniform(x[0], x[-1], 1500))
+    assert same_bits(plan.grid(xi2, yi), oracle.interp2_grid(x, y, z, xi2, yi))     # larger: re-allocates
+    z3 = plan.scattered(tx, ty); torch.cuda.synchronize()
+    assert same_bits(z3.cpu().numpy(), ref)
+    plan.close()
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
