@@ -1,4 +1,5 @@
 // common.cu — status/error plumbing and device helpers of the C-ABI (include/b200_common.h).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -7,6 +8,8 @@
 namespace b200 {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+unsigned long long count_launch() { return ++g_launches; }
 
 int fail(int status, const char* fmt, ...) {
   va_list ap;
@@ -49,6 +52,8 @@ int require_device() {
 extern "C" {
 
 const char* b200_last_error(void) { return b200::g_err; }
+
+unsigned long long b200_launch_count(void) { return b200::g_launches.load(); }
 
 int b200_version(void) { return (0 << 16) | (1 << 8) | 0; }
 

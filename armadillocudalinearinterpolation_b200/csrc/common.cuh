@@ -22,6 +22,11 @@ int require_device();
     cudaError_t e__ = (call);                                                   \
     if (e__ != cudaSuccess) return ::b200::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
+// every kernel launch of the library goes through B200_CNT(stream) in its launch configuration, so
+// b200_launch_count() (include/b200_common.h) is an exact count of this library's own launches
+unsigned long long count_launch();
+inline cudaStream_t counted_stream(cudaStream_t s) { count_launch(); return s; }
+#define B200_CNT(stream) ::b200::counted_stream(stream)
 #define B200_TRY(call)                \
   do {                                \
     int s__ = (call);                 \

@@ -995,7 +995,7 @@ int ensure_ensemble(b200_edm* h, cudaStream_t st) {
   if (h->w_dirty) {
     cudaFree(h->w); h->w = nullptr;
     B200_CUDA(cudaMalloc(&h->w, (size_t)h->N * sizeof(T)));
-    edm_coupling_kernel<T><<<(h->N + 255) / 256, 256, 0, st>>>(make_consts<T>(h), h->N, (T*)h->w);
+    edm_coupling_kernel<T><<<(h->N + 255) / 256, 256, 0, B200_CNT(st)>>>(make_consts<T>(h), h->N, (T*)h->w);
     B200_CUDA(cudaGetLastError());
     h->w_dirty = false;
   }
@@ -1004,7 +1004,7 @@ int ensure_ensemble(b200_edm* h, cudaStream_t st) {
       cudaFree(h->beta); h->beta = nullptr;
       const size_t n = (size_t)h->R * h->N;
       B200_CUDA(cudaMalloc(&h->beta, n * sizeof(T)));
-      edm_beta_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((T*)h->beta, n, h->params[0], h->sigma, h->seed);
+      edm_beta_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, B200_CNT(st)>>>((T*)h->beta, n, h->params[0], h->sigma, h->seed);
       B200_CUDA(cudaGetLastError());
       h->beta_dirty = false;
     }
@@ -1029,7 +1029,7 @@ int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaSt
   if (smem > 227 * 1024) return fail(B200_ERR_UNSUPPORTED, "no_neurons=%u / no_fronts=%u need %zu B of shared memory (max 232448)", h->N, h->Mf, smem);
   auto go = [&](auto kern) -> int {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)nitems, threads, smem, st>>>(A);
+    kern<<<(unsigned)nitems, threads, smem, B200_CNT(st)>>>(A);
     return B200_OK;
   };
   // 128-thread CTAs capped at 64 registers: 8 rings resident per SM, i.e. 8 serial Newton
@@ -1071,7 +1071,7 @@ template <typename T>
 int run_prepare(b200_edm* h, size_t ncols, cudaStream_t st) {
   B200_CUDA(cudaMemsetAsync(h->d_clamped, 0, sizeof(int32_t), st));
   if (h->profile_nc) {
-    edm_profile_lift_kernel<T><<<(unsigned)ncols, 256, 0, st>>>(make_consts<T>(h), h->N, h->profile_nc, h->d_z,
+    edm_profile_lift_kernel<T><<<(unsigned)ncols, 256, 0, B200_CNT(st)>>>(make_consts<T>(h), h->N, h->profile_nc, h->d_z,
                                                                 (T*)h->d_uc, (T*)h->d_lv, (T*)h->d_ls);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
@@ -1080,7 +1080,7 @@ int run_prepare(b200_edm* h, size_t ncols, cudaStream_t st) {
   if (smem > 200 * 1024) return fail(B200_ERR_UNSUPPORTED, "no_fronts=%u too large for the lift kernel", h->Mf);
   auto kern = edm_prepare_kernel<T>;
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)ncols, 256, smem, st>>>(make_consts<T>(h), h->N, h->Mf, (T)h->params[0], h->d_z,
+  kern<<<(unsigned)ncols, 256, smem, B200_CNT(st)>>>(make_consts<T>(h), h->N, h->Mf, (T)h->params[0], h->d_z,
                                            h->d_init, h->d_clamped, (T*)h->d_lv, (T*)h->d_ls);
   B200_CUDA(cudaGetLastError());
   return B200_OK;
@@ -1118,11 +1118,11 @@ template <typename T>
 int run_reduce(b200_edm* h, size_t ncols, const T* pos, const int32_t* accept, double* f_cols, cudaStream_t st) {
   if (h->profile_nc) {
     const size_t n = ndim(h), total = ncols * n;
-    edm_profile_reduce_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->R, (unsigned)n, ncols, h->d_z, pos, accept, f_cols);
+    edm_profile_reduce_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, B200_CNT(st)>>>(h->R, (unsigned)n, ncols, h->d_z, pos, accept, f_cols);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
   }
-  edm_reduce_kernel<T><<<(unsigned)ncols, 256, 0, st>>>(h->R, h->Mf, (double)(T)h->model.time_horizon,
+  edm_reduce_kernel<T><<<(unsigned)ncols, 256, 0, B200_CNT(st)>>>(h->R, h->Mf, (double)(T)h->model.time_horizon,
                                                         h->model.quirks, h->d_z, pos, accept, f_cols, h->d_mean);
   B200_CUDA(cudaGetLastError());
   return B200_OK;
@@ -1326,7 +1326,7 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
       B200_CUDA(cudaEventRecord(g->ev_up, gs));
       g->up_pending = true;
       const size_t total = cols_loc * n;
-      edm_fd_columns_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, gs>>>(
+      edm_fd_columns_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, B200_CNT(gs)>>>(
           g->d_u, (unsigned)n, eps, (unsigned)c_lo, (unsigned)cols_res, g->d_z);
       B200_CUDA(cudaGetLastError());
     } else {
@@ -1347,7 +1347,7 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
       if (fd) {
         B200_TRY(run_reduce<T>(g, cols_loc, (const T*)g->d_pos, g->d_accept, g->d_f, gs));
         const size_t total = cols_res * n;
-        edm_fd_jacobian_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, gs>>>(
+        edm_fd_jacobian_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, B200_CNT(gs)>>>(
             g->d_f, (unsigned)n, (unsigned)cols_res, pow(eps, -1), slot);
         B200_CUDA(cudaGetLastError());
       } else {
@@ -1377,7 +1377,7 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
         B200_CUDA(cudaMalloc(&h->d_jac, total * sizeof(double)));
         h->jac_cap = total;
       }
-      edm_fd_jacobian_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, st>>>(
+      edm_fd_jacobian_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, B200_CNT(st)>>>(
           h->d_f, (unsigned)n, (unsigned)ncols, pow(eps, -1), h->d_jac);
       B200_CUDA(cudaGetLastError());
       d_result = h->d_jac;
@@ -1654,7 +1654,7 @@ int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     B200_TRY(run_prepare<float>(h, ncols, st));
     B200_TRY(run_evolve<float>(h, item_begin, item_end, (float*)h->d_pos, accept_dev, st));
     if (nitems)
-      convert_kernel<float, double><<<(unsigned)((nitems * ndim(h) + 255) / 256), 256, 0, st>>>((const float*)h->d_pos, pos_dev, nitems * ndim(h));
+      convert_kernel<float, double><<<(unsigned)((nitems * ndim(h) + 255) / 256), 256, 0, B200_CNT(st)>>>((const float*)h->d_pos, pos_dev, nitems * ndim(h));
     B200_CUDA(cudaGetLastError());
   }
   h->last_cols = ncols;
@@ -1681,7 +1681,7 @@ int b200_edm_reduce_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     // accumulated in float exactly as the single-GPU path does
     const size_t nitems = ncols * h->R;
     B200_TRY(ensure_batch(h, ncols, nitems));
-    convert_kernel<double, float><<<(unsigned)((nitems * ndim(h) + 255) / 256), 256, 0, st>>>(pos_all_dev, (float*)h->d_pos, nitems * ndim(h));
+    convert_kernel<double, float><<<(unsigned)((nitems * ndim(h) + 255) / 256), 256, 0, B200_CNT(st)>>>(pos_all_dev, (float*)h->d_pos, nitems * ndim(h));
     B200_TRY(run_reduce<float>(h, ncols, (const float*)h->d_pos, accept_all_dev, f_cols_dev, st));
   }
   return mark_done(h, st);

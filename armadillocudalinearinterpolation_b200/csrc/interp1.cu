@@ -185,7 +185,7 @@ template <> Axis<float>& axis_of<float>(b200_interp1_plan* p) { return p->ax32; 
 template <typename T>
 int plan1_build_seg(b200_interp1_plan* p, cudaStream_t st) {
   Axis<T>& A = axis_of<T>(p);
-  build_seg1_kernel<T><<<grid_for(p->ng), kThreads, 0, st>>>(A.x, (const T*)p->yg, (int)p->ng,
+  build_seg1_kernel<T><<<grid_for(p->ng), kThreads, 0, B200_CNT(st)>>>(A.x, (const T*)p->yg, (int)p->ng,
                                                              (T*)p->seg);
   B200_CUDA(cudaGetLastError());
   return B200_OK;
@@ -234,7 +234,7 @@ int plan1_launch(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* i
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
       const size_t blocks = (nvec + kSmem1Threads - 1) / kSmem1Threads;
       const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
-      kern<<<(int)(blocks < resident ? blocks : resident), kSmem1Threads, p->smem_bytes, st>>>(
+      kern<<<(int)(blocks < resident ? blocks : resident), kSmem1Threads, p->smem_bytes, B200_CNT(st)>>>(
           ax, (const T*)p->yg, xi, yi, idx, nvec, extrap);
       return B200_OK;
     };
@@ -247,16 +247,16 @@ int plan1_launch(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* i
     static const size_t forced = [] { const char* e = getenv("B200_INTERP1_GRID_MULT"); return (size_t)(e && atoi(e) > 0 ? atoi(e) : 0); }();
     const size_t mult = forced ? forced : (blocks > (size_t)148 * 256 ? 64 : 16);
     int grid = (int)(blocks < (size_t)148 * mult ? blocks : (size_t)148 * mult);
-    if (idx) interp1_vec_kernel<T, true><<<grid, kThreads, 0, st>>>(ax, seg, xi, yi, idx, nvec, extrap);
-    else interp1_vec_kernel<T, false><<<grid, kThreads, 0, st>>>(ax, seg, xi, yi, nullptr, nvec, extrap);
+    if (idx) interp1_vec_kernel<T, true><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, xi, yi, idx, nvec, extrap);
+    else interp1_vec_kernel<T, false><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, xi, yi, nullptr, nvec, extrap);
   }
   size_t done = nvec * V;
   if (done < ni) {
     size_t rem = ni - done;
     size_t blocks = (rem + kThreads - 1) / kThreads;
     int grid = (int)(blocks < (size_t)148 * 64 ? blocks : (size_t)148 * 64);
-    if (idx) interp1_scalar_kernel<T, true><<<grid, kThreads, 0, st>>>(ax, seg, xi, yi, idx, done, ni, extrap);
-    else interp1_scalar_kernel<T, false><<<grid, kThreads, 0, st>>>(ax, seg, xi, yi, nullptr, done, ni, extrap);
+    if (idx) interp1_scalar_kernel<T, true><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, xi, yi, idx, done, ni, extrap);
+    else interp1_scalar_kernel<T, false><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, xi, yi, nullptr, done, ni, extrap);
   }
   B200_CUDA(cudaGetLastError());
   return B200_OK;

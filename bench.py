@@ -42,6 +42,30 @@ Z_DRIVER = np.array([np.float32(0.3310), np.float32(0.6914), np.float32(1.3557)]
 BETA = float(np.float32(13.0589))
 
 
+def headline_config(n_gpus):
+    """`config` of the JSON line — identical for this implementation and for --impl reference
+    (the driver compares the two arms' configs)."""
+    return {"workload": WORKLOAD,
+            "grid": GRID_DESC,
+            "queries": "1e8 (x,y) ~ U[0,1]^2 per GPU, unsorted, seed 2235+rank",
+            "l2": "inputs larger than L2 (1.6 GB of queries + 0.8 GB of outputs per step)",
+            "parallelism": f"query shards x{n_gpus}, no collective"}
+
+
+def source_stamp(files):
+    """sha1 over the kernel sources a static ncu figure was captured for (staleness check)."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in files:
+        with open(os.path.join(ROOT, "armadillocudalinearinterpolation_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+INTERP2_SOURCES = ("interp2.cu", "interp_common.cuh", "common.cuh")
+EDM_SOURCES = ("edm.cu", "common.cuh")
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -140,24 +164,32 @@ def cpu_interp2(sample, threads, grid=None):
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  Armadillo is absent
     from the image and the reference has no interp2 call site, so this is the
-    oracle port of arma::interp2's algorithm, all host threads, bounded sample per step."""
+    oracle port of arma::interp2's algorithm on all host threads.  One step = a bounded sample
+    (2e7 of the 1e8 queries); --warmup W untimed and exactly --steps K timed steps, like the other arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = cpu_threads()
     grid = make_grid()
     sample = 20_000_000
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_interp2(2_000_000, threads, grid)
-    vals = [cpu_interp2(sample, threads, grid) for _ in range(max(1, min(args.steps, 5)))]
-    v = float(np.mean(vals))
+    from oracle import oracle_py as O
+    x, y, z = grid
+    rng = np.random.default_rng(2235)
+    xq = rng.random(sample); yq = rng.random(sample)
+    for _ in range(max(args.warmup, 0)):
+        O.interp2_scattered(x, y, z, xq, yq, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.interp2_scattered(x, y, z, xq, yq, nthreads=threads)
+    sec = (time.perf_counter() - t0) / args.steps
+    v = sample / sec
     line = {"impl": "reference", "metric": METRIC,
-            "value": v, "unit": "points/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1,
-            "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "value": v, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "grid": GRID_DESC, "sample": f"{sample} queries per step (of 1e8)"},
+            "config": headline_config(args.gpus),
             "cpu_baseline": {"value": v, "unit": "points/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} of 1e8 scattered queries, OpenMP over queries"},
+                             "sample": f"{sample} of the 1e8 scattered queries per step, oracle restatement of arma::interp2, OpenMP over queries"},
             "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -214,12 +246,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--config5-full", action="store_true", help="profile-map stability at R = 1000 (1e6 neurons per column)")
+    ap.add_argument("--config5-full", action="store_true", help="(default now) profile-map stability at R = 1000 (1e6 neurons per column)")
+    ap.add_argument("--no-config5-full", action="store_true", help="skip the R = 1000 profile-map stability")
     ap.add_argument("--only-config5", action="store_true", help="of the secondary workloads run only the profile-map stability")
     args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)      # both arms: at least 3 warm-up steps
     if args.impl == "reference":
         return run_reference(args)
-    args.warmup = max(args.warmup, 3)
 
     import torch
     import armadillocudalinearinterpolation_b200 as B
@@ -231,6 +264,7 @@ def main():
     torch.cuda.set_device(local)
     B.set_device(local)
     dist = None
+    cpu_group = None
     if world > 1:
         # keep stdout to the one JSON line (NCCL prints its version banner there otherwise)
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -238,6 +272,7 @@ def main():
         import torch.distributed as dist_
         dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_
+        cpu_group = dist.new_group(backend="gloo")     # host-side waits (no GPU kernel spinning on an idle rank's device)
     n_gpus = world
 
     # ---------------- headline: interp2 scattered, 1e8 queries / GPU ----------------
@@ -249,20 +284,32 @@ def main():
     zq = torch.empty_like(xq)
     step = lambda: plan.scattered(xq, yq, out=zq)
     sampler = ClockSampler(local)
+    from armadillocudalinearinterpolation_b200 import _lib as L_
+    L_.lib().b200_launch_count.restype = C.c_ulonglong
     time_steps(torch, step, 1, args.warmup, dist)       # warm-up outside the sampled window
     sampler.start()
+    launches0 = L_.lib().b200_launch_count()
     ms = time_steps(torch, step, args.steps, 0, dist)
+    gpu_launches = int(L_.lib().b200_launch_count() - launches0)   # counted by the library at every launch site
     clocks = sampler.stop()
     ms_per_step = ms / args.steps
     value = n_gpus * NQ / (ms_per_step * 1e-3)
     peak, peak_src = measured_peak()
     alg_bytes = ALG_BYTES_PER_QUERY * NQ + ALG_BYTES_GRID
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic = None
+    # dram__bytes of the same kernel from the committed ncu capture (tools/make_profiles.py); the capture
+    # carries a hash of the kernel sources it was taken for, so a stale figure is flagged, not silently reused
+    traffic, traffic_note = None, "no ncu capture committed"
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("interp2_scattered_f64", {}).get("dram_bytes_per_launch")
+            rec = json.load(open(tpath)).get("interp2_scattered_f64", {})
+            traffic = rec.get("dram_bytes_per_launch")
+            stamp = rec.get("source_sha1")
+            now = source_stamp(INTERP2_SOURCES)
+            traffic_note = (f"ncu --set full capture {rec.get('capture', '?')}, kernel sources unchanged since (sha1 {now})"
+                            if stamp == now else
+                            f"STALE: captured for kernel sources {stamp}, this build is {now}")
         except Exception:
             traffic = None
 
@@ -276,13 +323,19 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = wall_steps(torch, lambda: plan.scattered(hxn, hyn, out=hzn), e2e_steps, 1, dist) / e2e_steps
     e2e_val = n_gpus * NQ / (e2e_ms * 1e-3)
-    check = float(np.abs(hzn[:1000] - zq[:1000].cpu().numpy()).max())
-    del hx, hy, hz
+    zq_host = zq.cpu().numpy()
+    check_all_bits = bool(np.array_equal(hzn.view(np.int64), zq_host.view(np.int64)))   # all 1e8 outputs, bit for bit
+    check = float(np.nanmax(np.abs(hzn - zq_host)))
+    # the same call with PAGEABLE buffers (what a plain arma::vec is): staged through the library's pinned ring
+    pxn, pyn, pzn = np.array(hxn), np.array(hyn), np.empty_like(hzn)
+    pg_steps = 3
+    pg_ms = wall_steps(torch, lambda: plan.scattered(pxn, pyn, out=pzn), pg_steps, 1, dist) / pg_steps
+    pageable_bits = bool(np.array_equal(pzn.view(np.int64), zq_host.view(np.int64)))
+    del hx, hy, hz, pxn, pyn, pzn, zq_host
 
     # machine ceiling for this access pattern, measured live: independent 32-byte gathers from a
     # 512 MiB table (every L2 miss fills a 128-byte line on B200, so uniformly random queries are
     # bounded by this, not by the streaming copy rate)
-    from armadillocudalinearinterpolation_b200 import _lib as L_
     g_ms, g_rate = L_.bench_random_gather(512 << 20, NQ)
     tile_bytes = (((NX - 1) // 3 + 1) * ((NY - 1) // 3 + 1)) * 128      # the table the kernel actually gathers from
     g2_ms, g2_rate = L_.bench_random_gather(tile_bytes, NQ)
@@ -292,20 +345,30 @@ def main():
             "value": value, "unit": "points/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "grid": GRID_DESC,
-                       "queries": "1e8 (x,y) ~ U[0,1]^2 per GPU, unsorted, seed 2235+rank",
-                       "l2": "inputs larger than L2 (1.6 GB of queries + 0.8 GB of outputs per step)",
-                       "layout": "linspace axes recognised as affine at plan time (knots recomputed in registers; other axes are staged in shared memory by TMA bulk copy); Z as overlapping 4x4 tiles, one 128-byte line per cell (228 MiB)",
-                       "parallelism": f"query shards x{n_gpus}, no collective"},
-            "gpu_launches": args.steps,
+            "config": headline_config(n_gpus),
+            "layout": "linspace axes recognised as affine at plan time (knots recomputed in registers; other axes are staged in shared memory by TMA bulk copy); Z as overlapping 4x4 tiles, one 128-byte line per cell (228 MiB)",
+            "gpu_launches": gpu_launches,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "points/s", "h2d_bytes_per_step": 16 * NQ, "d2h_bytes_per_step": 8 * NQ,
                     "ms_per_step": e2e_ms, "api": "b200_interp2_scattered (pinned host buffers, 2-slot chunked pipeline)",
-                    "max_abs_diff_vs_device_path": check},
+                    "all_1e8_outputs_bitwise_equal_to_device_path": check_all_bits,
+                    "max_abs_diff_vs_device_path": check,
+                    "pageable_host_buffers": {"value": n_gpus * NQ / (pg_ms * 1e-3), "ms_per_step": pg_ms,
+                                              "bitwise_equal": pageable_bits,
+                                              "note": "same call with ordinary (pageable) numpy / arma::vec buffers"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "interp2_scattered_smem_kernel<double, tiles>",
+                         "traffic": traffic, "traffic_source": traffic_note,
+                         "peak_source": peak_src, "kernel": "interp2_scattered_smem_kernel<double, tiles>",
                          "algorithmic_bytes_per_launch": alg_bytes,
+                         # what bounds uniformly random queries on a 128 MiB grid, as numbers: one table line per
+                         # query is the minimum (four corners in one 128-byte line), and this GPU delivers random
+                         # lines from a table of this size at the rate measured live below — the floor is the
+                         # slower of that and the HBM streaming time of the algorithmic bytes
+                         "floor": {"ms": max(1e3 * alg_bytes / (peak * 1e9), g2_ms),
+                                   "hbm_stream_ms": 1e3 * alg_bytes / (peak * 1e9),
+                                   "random_line_gather_ms": g2_ms,
+                                   "derivation": "max(algorithmic bytes / measured HBM copy peak, 1e8 / measured random 32-byte gather rate from a table of the tile table's size [b200_bench_random_gather, same run])"},
+                         "frac_of_floor": max(1e3 * alg_bytes / (peak * 1e9), g2_ms) / ms_per_step,
                          "random_gather_ceiling": {"gathers_per_s": g_rate, "ms_for_1e8": g_ms,
                                                    "frac_of_ceiling": (NQ / (ms_per_step * 1e-3)) / g_rate,
                                                    "note": "1e8 independent 32-byte gathers from a 512 MiB table (the size of the 2x2 corner records), same GPU, same run"},
@@ -412,7 +475,13 @@ def main():
             extra["interp2_scattered_f64_cell_sorted_queries"] = {"points_per_s": n_gpus * NQ / (mss * 1e-3), "ms_per_launch": mss,
                                                                   "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
             del xs, ys
-            # configs[2]: one map evaluation, parameters.hpp default ensemble (R=1000, N=1024, M=3, T=5)
+            # configs[2]: one map evaluation, parameters.hpp default ensemble (R=1000, N=1024, M=3, T=5).
+            # Roofline convention frozen in BASELINE.md §3: unit of work = neuron-event update, F_alg = 10 FP64
+            # flops per update (calibrated once against ncu SASS op counts: (2 dfma + dadd + dmul) / updates = 9.8),
+            # peak = the FP64 FMA issue ceiling measured live by b200_bench_fp64_fma.  The event loop is a serial
+            # dependency chain, so the fraction is low by construction; chain_cycles_per_event says how long one
+            # event of one ring takes end to end.
+            F_ALG = 10.0
             for sigma in (0.0, 0.5):
                 m = B.EventDrivenMap([BETA], 1000, noNeurons=1024)
                 m.SetParameterStdDev(sigma); m.SetSeed(42); m.EnableTiming(True)
@@ -426,12 +495,32 @@ def main():
                     evolve_ms.append(m.LastEvolveMs())
                 call_ms = 1e3 * (time.perf_counter() - t0) / reps
                 cnt = m.LastCounters()
-                extra[f"map_eval_R1000_N1024_sigma{sigma}"] = {
-                    "evals_per_s_per_gpu": 1e3 / call_ms, "ms_per_compute_f": call_ms, "evolve_kernel_ms": float(np.mean(evolve_ms)),
-                    "events": cnt["events"], "neuron_event_updates_per_s": cnt["events"] * 1024 / (np.mean(evolve_ms) * 1e-3),
+                ev_ms = float(np.mean(evolve_ms))
+                updates = cnt["events"] * 1024
+                tflops = updates * F_ALG / (ev_ms * 1e-3) / 1e12
+                rec = {
+                    "evals_per_s_per_gpu": 1e3 / call_ms, "ms_per_compute_f": call_ms, "evolve_kernel_ms": ev_ms,
+                    "events": cnt["events"], "neuron_event_updates_per_s": updates / (ev_ms * 1e-3),
                     "candidates": cnt["candidates"], "newton_its": cnt["newton_its"],
-                    "fp64_fma_peak_tflops_measured": fp64_peak}
+                    "roofline": {"bound": "fp64 pipe (latency-bound in practice)", "achieved": tflops, "peak": fp64_peak,
+                                 "unit": "TFLOP/s", "frac": tflops / fp64_peak,
+                                 "convention": "10 FP64 flops per neuron-event update (BASELINE.md §3), peak = live DFMA issue ceiling",
+                                 "chain_cycles_per_event": ev_ms * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / (cnt["events"] / 1000.0)}}
                 m.close()
+                if rank == 0 and n_gpus == 1 and not args.no_cpu:
+                    # CPU baseline of the same evaluation: the oracle's restatement of lift -> evolve -> restrict,
+                    # OpenMP over realisations, on a bounded sample of the 1000 realisations
+                    from oracle import oracle_py as O
+                    th = cpu_threads()
+                    rs = 2 * th
+                    cfg = O.edm_cfg(R=1000, N=1024, sigma=sigma, seed=42)
+                    O.edm_compute_f(cfg, Z_DRIVER, r_begin=0, r_end=th, nthreads=th, aux=False)
+                    tc = time.perf_counter()
+                    O.edm_compute_f(cfg, Z_DRIVER, r_begin=0, r_end=rs, nthreads=th, aux=False)
+                    sec = (time.perf_counter() - tc) * 1000.0 / rs          # seconds per full 1000-realisation evaluation
+                    rec["cpu_baseline"] = {"value": 1.0 / sec, "unit": "map evals/s", "cores": th, "kind": "port",
+                                           "sample": f"{rs} of the 1000 realisations, scaled; oracle restatement of EventDrivenMap::ComputeF"}
+                extra[f"map_eval_R1000_N1024_sigma{sigma}"] = rec
             # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
             # items sharded over the ranks, positions gathered with one NCCL all-gather
             jm = parallel.ShardedJacobian([BETA], 1000, noNeurons=1024, group=dist)
@@ -452,21 +541,84 @@ def main():
         nc = 500
         xf = -3.0 + 6.0 / 1024 * np.arange(1024); xc = -3.0 + 6.0 / nc * np.arange(nc)
         u0 = np.concatenate([np.interp(xc, xf, lv), np.interp(xc, xf, ls)])
-        R5 = 1000 if args.config5_full else 64
-        pj = parallel.ShardedJacobian([BETA], R5, noNeurons=1024, group=dist, shard="columns")
-        pj.engine.map.SetTimeHorizon(1.0)
-        pj.SetProfileMode(nc)
-        J5 = pj.ComputeDFDU(u0, 1e-3)
-        reps5 = 1 if args.config5_full else 3
-        ms5 = wall_steps(torch, lambda: pj.ComputeDFDU(u0, 1e-3), reps5, 0, dist) / reps5
-        t0 = time.perf_counter()
-        lam = np.linalg.eigvals(J5 + np.eye(2 * nc)) if rank == 0 else None
-        eig_ms = 1e3 * (time.perf_counter() - t0)
-        extra[f"profile_stability_n1000_N1024_R{R5}"] = {
-            "ms_per_jacobian": ms5, "map_evals_per_s": 1001e3 / ms5, "columns": 1001, "rings": 1001 * R5,
-            "neurons_per_column": 1024 * R5, "time_horizon": 1.0, "ranks": n_gpus, "scaling": "strong",
-            "unstable_eigenvalues": int(np.sum(np.abs(lam) > 1.0)) if rank == 0 else None,
-            "host_eig_ms": eig_ms, "collective": "all_gather of 1001 residual columns (8 MB)" if world > 1 else "none"}
+        for R5 in ([64] if args.no_config5_full else [64, 1000]):   # R = 1000: 1e6 neurons per column (BASELINE config 5)
+            pj = parallel.ShardedJacobian([BETA], R5, noNeurons=1024, group=dist, shard="columns")
+            pj.engine.map.SetTimeHorizon(1.0)
+            pj.SetProfileMode(nc)
+            J5 = pj.ComputeDFDU(u0, 1e-3)
+            reps5 = 1 if R5 >= 1000 else 3
+            ms5 = wall_steps(torch, lambda: pj.ComputeDFDU(u0, 1e-3), reps5, 0, dist) / reps5
+            t0 = time.perf_counter()
+            lam = np.linalg.eigvals(J5 + np.eye(2 * nc)) if rank == 0 else None
+            eig_ms = 1e3 * (time.perf_counter() - t0)
+            extra[f"profile_stability_n1000_N1024_R{R5}"] = {
+                "ms_per_jacobian": ms5, "map_evals_per_s": 1001e3 / ms5, "columns": 1001, "rings": 1001 * R5,
+                "neurons_per_column": 1024 * R5, "time_horizon": 1.0, "ranks": n_gpus, "scaling": "strong",
+                "unstable_eigenvalues": int(np.sum(np.abs(lam) > 1.0)) if rank == 0 else None,
+                "host_eig_ms_numpy": eig_ms, "collective": "all_gather of 1001 residual columns (8 MB)" if world > 1 else "none",
+                "launcher": "one process per GPU (torchrun), torch.distributed NCCL all_gather_into_tensor"}
+            pj.engine.map.close()
+            del pj
+        # ---- configs[3] and [4] through the product's own C++ classes (host layer over the C-ABI) ----
+        # Rank 0 drives 1 and then all n_gpus devices IN ONE PROCESS (EventDrivenMapB200::SetDevices: column / item
+        # shards, one ncclAllGather inside libb200edm.so); the other ranks wait on the host (gloo), their GPUs idle.
+        cpp = {}
+        try:
+          if rank == 0:
+            host = C.CDLL(os.path.join(ROOT, "armadillocudalinearinterpolation_b200", "lib", "libb200host.so"))
+            host.b200_host_last_error.restype = C.c_char_p
+            dp = lambda a: a.ctypes.data_as(C.c_void_p)
+            dev_sets = [1] + ([n_gpus] if n_gpus > 1 else [])
+
+            def newton(ndev):
+                sol = np.zeros(3); hist = np.full(11, np.nan); nh = C.c_int(); J = np.zeros((3, 3), order="F"); msv = np.zeros(2)
+                devs = (C.c_int * ndev)(*range(ndev))
+                rc = host.b200_host_edm_newton_multi(C.c_double(BETA), 1000, 1024, dp(Z_DRIVER), 3, C.c_double(1e-4), 10,
+                                                     C.c_double(1e-2), 1, C.c_double(0.0), ndev, devs, dp(sol), dp(hist),
+                                                     C.byref(nh), dp(J), dp(msv))
+                if rc < 0:
+                    raise RuntimeError(host.b200_host_last_error().decode())
+                return rc, sol, hist[:nh.value], J, msv
+
+            res = {nd: newton(nd) for nd in dev_sets}
+            r1 = res[1]
+            cpp["newton_config4_R1000_N1024"] = {
+                "driver_settings": "Driver.cu:28-37 (tol 1e-4, <= 10 iterations, FD eps 1e-2), Jacobian through ComputeDFDU",
+                "converged": bool(r1[0] == 1), "iterations": int(len(r1[2]) - 1), "solution": r1[1].tolist(),
+                "final_residual": float(r1[2][-1]),
+                "solve_ms": {str(nd): float(res[nd][4][0]) for nd in dev_sets},
+                "jacobian_ms": {str(nd): float(res[nd][4][1]) for nd in dev_sets},
+                "bitwise_equal_across_device_counts": all(
+                    np.array_equal(res[nd][1], r1[1]) and np.array_equal(res[nd][2], r1[2]) and np.array_equal(res[nd][3], r1[3])
+                    for nd in dev_sets)}
+
+            def stability(R, ndev):
+                n = 2 * nc
+                msv = np.zeros(3); J = np.zeros((n, n), order="F"); re = np.zeros(n); im = np.zeros(n)
+                devs = (C.c_int * ndev)(*range(ndev))
+                cnt = host.b200_host_profile_stability(C.c_double(BETA), R, 1024, nc, C.c_double(1.0), dp(u0), C.c_double(1e-3),
+                                                       ndev, devs, dp(msv), dp(J), dp(re), dp(im))
+                if cnt <= -1000:
+                    raise RuntimeError(host.b200_host_last_error().decode())
+                return cnt, J, msv
+
+            for R in ([64] if args.no_config5_full else [64, 1000]):
+                sres = {nd: stability(R, nd) for nd in dev_sets}
+                s1 = sres[1]
+                lam_np = np.linalg.eigvals(s1[1] + np.eye(2 * nc))
+                cpp[f"stability_config5_n1000_N1024_R{R}"] = {
+                    "call": "Stability::ComputeNumUnstableEigenvalues(u) = FD Jacobian (1001 evaluations) + arma::eig_gen (cuSOLVER GEEV behind the shim)",
+                    "neurons_per_column": 1024 * R, "unstable_eigenvalues": int(s1[0]),
+                    "numpy_count_on_same_jacobian": int(np.sum(np.abs(lam_np) > 1.0)),
+                    "whole_call_ms": {str(nd): float(sres[nd][2][0]) for nd in dev_sets},
+                    "jacobian_ms": {str(nd): float(sres[nd][2][1]) for nd in dev_sets},
+                    "eig_gen_ms": {str(nd): float(sres[nd][2][2]) for nd in dev_sets},
+                    "bitwise_equal_across_device_counts": all(np.array_equal(sres[nd][1], s1[1]) and sres[nd][0] == s1[0] for nd in dev_sets)}
+        except Exception as e:      # the headline line must still be printed
+            cpp["error"] = f"{type(e).__name__}: {e}"
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
+        extra["cpp_host_layer"] = cpp
         line["extra"] = extra
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------

@@ -36,6 +36,10 @@ const char* b200_last_error(void);
 /* Library/ABI version: (major<<16)|(minor<<8)|patch. */
 int b200_version(void);
 
+/* Number of kernels this library has launched so far in this process (every launch site counts itself):
+ * the bench reports the difference over its timed region as `gpu_launches`. */
+unsigned long long b200_launch_count(void);
+
 /* Number of visible CUDA devices (<=0: none — every compute entry point then fails
  * with B200_ERR_NO_DEVICE; nothing in this library computes on the host). */
 int b200_device_count(void);

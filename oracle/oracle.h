@@ -4,15 +4,17 @@
  * legs may load this library, and only as the checker / the timed CPU baseline.  The
  * product (armadillocudalinearinterpolation_b200/) never links, imports or calls it.
  *
- * PARITY UNPINNED.  The reference ships no tests, golden vectors or fixtures, and it
- * cannot be built here (no Armadillo on disk, sm_30 build flags, removed __shfl_down,
- * undefined `counterMax` at EventDrivenMap.cu:564 — SURVEY.md §8c).  Every function
- * below is a restatement written from the reference sources (file:line cited at each
- * function) or, for interp1/interp2, from Armadillo's published algorithm
- * (fn_interp1.hpp / fn_interp2.hpp; Armadillo is an un-vendored, un-pinned dependency
- * of the reference: Makefile:5 `-larmadillo`, Driver.o.dep:554).  The only pins are the
- * survey's independent NumPy emulation values (tests/golden/) and
- * numpy.interp / scipy second opinions.
+ * PARITY.
+ *   map (edm_*): PINNED against the real reference.  oracle/ref_build/Makefile compiles the UNMODIFIED
+ *     EventDrivenMap.cu / NewtonSolver.cpp / Stability.cpp for sm_100a (two macros: `counterMax` = 100, which
+ *     EventDrivenMap.cu:564 leaves undefined, and `__shfl_down` -> `__shfl_down_sync`) into oracle/_ref/; its raw
+ *     outputs on a B200 are committed as tests/golden/ref_b200.npz (tools/make_ref_golden.py).  The FP32 / Q1 mode
+ *     of this oracle reproduces them: every integer output exactly, floats to FP32 noise, and the reference
+ *     NewtonSolver's residual history (tests/test_ref_pin.py).  The FP64 mode is the same template.
+ *   interp1 / interp2: PARITY UNPINNED against Armadillo itself — an un-vendored, un-pinned dependency of the
+ *     reference (Makefile:5 `-larmadillo`, Driver.o.dep:554) that is absent from this image and that the
+ *     reference never calls for interpolation.  Restated from Armadillo's published algorithm
+ *     (fn_interp1.hpp / fn_interp2.hpp); second opinions: numpy.interp, scipy RegularGridInterpolator.
  *
  * Compile with -O2 -ffp-contract=off (no FMA contraction) — see oracle/Makefile.
  */

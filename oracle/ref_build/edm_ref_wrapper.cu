@@ -18,6 +18,7 @@
 #include "Stability.hpp"
 #undef private
 #include <cstring>
+#include <exception>
 #include <vector>
 
 namespace {
@@ -119,16 +120,18 @@ int edm_ref_newton(double beta, unsigned R, int N, float T, float sigma, unsigne
   pars.damping = damping;
   NewtonSolver* ns = new NewtonSolver(m, &guess, &pars);
   pars.finiteDifferenceEpsilon = fd_epsilon;             /* set after construction, as Driver.cu:37 */
-  AbstractNonlinearSolver::ExitFlagType flag;
+  AbstractNonlinearSolver::ExitFlagType flag = AbstractNonlinearSolver::ExitFlagType::notConverged;
   arma::mat jac(noSpikes, noSpikes);
-  unsigned long long keep = m->mSeed;
-  ns->Solve(sol, hist, flag, &jac);
-  (void)keep;
+  /* the reference lets arma::solve's exception escape (a singular FD Jacobian aborts its driver): caught
+   * here so that the history up to that point can still be read; returns -2 */
+  bool threw = false;
+  try { ns->Solve(sol, hist, flag, &jac); } catch (const std::exception&) { threw = true; }
   for (int i = 0; i < noSpikes; ++i) z_out[i] = sol[i];
   for (int i = 0; i <= max_iterations; ++i) residual_history[i] = (i < (int)hist.n_elem) ? hist[i] : -1.0;
   if (jacobian_out) memcpy(jacobian_out, jac.memptr(), sizeof(double) * noSpikes * noSpikes);
   delete ns;
   delete m;
+  if (threw) return -2;
   return flag == AbstractNonlinearSolver::ExitFlagType::converged ? 0 : 1;
 }
 
@@ -142,7 +145,8 @@ int edm_ref_unstable(double beta, unsigned R, int N, float T, float sigma, unsig
   st->mFiniteDifferenceEpsilon = fd_epsilon;
   arma::vec Z(noSpikes);
   for (int i = 0; i < noSpikes; ++i) Z[i] = z[i];
-  int n = st->ComputeNumUnstableEigenvalues(Z);
+  int n = -2;
+  try { n = st->ComputeNumUnstableEigenvalues(Z); } catch (const std::exception&) {}
   /* ~Stability is declared but never defined in the reference (Stability.hpp:28): leak it, as Driver.cu does */
   delete m;
   return n;

@@ -219,3 +219,8 @@ def test_in_process_multi_device_is_bitwise_single_device(b200):
         m.SetTimeHorizon(0.5); m.SetProfileMode(64)
     u = np.concatenate([np.linspace(0.2, 0.95, 64), np.linspace(0.0, 0.5, 64)])
     assert np.array_equal(a.ComputeF(u), b.ComputeF(u))
+    # 128 columns over <= 4 devices: whole columns per device, local reduction, one all-gather of the columns
+    Ja, fa = a.ComputeDFDU(u, 1e-3, return_f0=True); Jb, fb = b.ComputeDFDU(u, 1e-3, return_f0=True)
+    assert np.array_equal(Ja, Jb) and np.array_equal(fa, fb)
+    uc = np.stack([u * (1 + 1e-3 * k) for k in range(40)], axis=1)
+    assert np.array_equal(a.ComputeFBatch(uc), b.ComputeFBatch(uc))

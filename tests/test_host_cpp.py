@@ -222,3 +222,89 @@ def test_interp1_adaptor_fvec(host, oracle):
     yi = np.empty_like(xi)
     assert host.b200_host_interp1_f32(dp(x), dp(y), x.size, dp(xi), xi.size, dp(yi), C.c_float(0.0)) == 0, host.b200_host_last_error()
     assert np.array_equal(yi, oracle.interp1(x, y, xi, extrap=0.0, want_idx=False))
+
+
+# ---- round 2: the eigen-solve behind arma::eig_gen, and configs 4 / 5 through the C++ classes ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [200, 1000])
+def test_eig_gen_backend_matches_numpy(host, n, monkeypatch):
+    """arma::eig_gen as Stability.cpp:40,72 calls it: for n >= 128 the shim hands the matrix to
+    b200_eig_gen_f64 (cuSOLVER GEEV on the device); same spectrum as numpy (LAPACK dgeev) and as the
+    shim's own Hessenberg-QR (B200_SHIM_HOST_EIG=1)."""
+    rng = np.random.default_rng(100 + n)
+    A = np.asfortranarray(rng.standard_normal((n, n)) / np.sqrt(n) + np.diag(np.linspace(0.2, 1.4, n)))
+    lam = np.sort_complex(np.linalg.eigvals(A))
+    re = np.zeros(n); im = np.zeros(n); ms = C.c_double()
+    for rep in range(2):
+        assert host.b200_host_eig_gen(n, dp(A), dp(re), dp(im), C.byref(ms)) == 0, host.b200_host_last_error()
+    print(f"eig_gen n={n}: {ms.value:.1f} ms (device backend, second call)")
+    got = np.sort_complex(re + 1j * im)
+    assert np.allclose(got, lam, rtol=1e-8, atol=1e-8)
+    assert int(np.sum(np.abs(got) > 1.0)) == int(np.sum(np.abs(lam) > 1.0))
+    if n <= 200:
+        monkeypatch.setenv("B200_SHIM_HOST_EIG", "1")
+        assert host.b200_host_eig_gen(n, dp(A), dp(re), dp(im), C.byref(ms)) == 0
+        assert np.allclose(np.sort_complex(re + 1j * im), lam, rtol=1e-8, atol=1e-8)
+
+
+def _newton_multi(host, R, N, ndev, mode=1, sigma=0.0):
+    n = 3
+    sol = np.zeros(n); hist = np.full(11, np.nan); nh = C.c_int(); J = np.zeros((n, n), order="F"); ms = np.zeros(2)
+    devs = (C.c_int * max(ndev, 1))(*range(max(ndev, 1)))
+    rc = host.b200_host_edm_newton_multi(C.c_double(BETA), R, N, dp(Z_DRIVER), n, C.c_double(1e-4), 10, C.c_double(1e-2),
+                                         mode, C.c_double(sigma), ndev, devs, dp(sol), dp(hist), C.byref(nh), dp(J), dp(ms))
+    assert rc >= 0, host.b200_host_last_error()
+    return rc, sol, hist[:nh.value], J, ms
+
+
+@pytest.mark.gpu
+def test_config4_newton_driver_settings_cpp(host, b200):
+    """BASELINE config 4 through the product's own C++ NewtonSolver with the reference driver's settings
+    (Driver.cu:28-37: tol 1e-4, <= 10 iterations, eps 1e-2, R = 1000, N = 1024): converges to the fixed point
+    pinned in tests/test_oracle_edm.py; with several GPUs in this process (SetDevices -> NCCL all-gather inside
+    libb200edm.so) every iterate is bitwise the single-GPU one."""
+    rc1, sol1, hist1, J1, ms1 = _newton_multi(host, 1000, 1024, 1)
+    assert rc1 == 1
+    assert np.allclose(sol1, [0.331444, 0.695637, 1.365721], atol=2e-6) and hist1[-1] < 1e-4
+    ndev = b200.device_count()
+    if ndev >= 2:
+        for sigma in (0.0, 0.3):
+            a = _newton_multi(host, 1000, 1024, 1, sigma=sigma)
+            b = _newton_multi(host, 1000, 1024, min(ndev, 8), sigma=sigma)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+
+
+def _profile_stability(host, R, N, nc, T, u, eps, ndev):
+    n = 2 * nc
+    ms = np.zeros(3); J = np.zeros((n, n), order="F"); re = np.zeros(n); im = np.zeros(n)
+    devs = (C.c_int * max(ndev, 1))(*range(max(ndev, 1)))
+    cnt = host.b200_host_profile_stability(C.c_double(BETA), R, N, nc, C.c_double(T), dp(u), C.c_double(eps), ndev, devs,
+                                           dp(ms), dp(J), dp(re), dp(im))
+    assert cnt > -1000, host.b200_host_last_error()
+    return cnt, J, re + 1j * im, ms
+
+
+@pytest.mark.gpu
+def test_config5_profile_stability_cpp(host, b200):
+    """BASELINE config 5 (small shape) through Stability::ComputeNumUnstableEigenvalues of the C++ host layer:
+    the Jacobian is the Python binding's, bit for bit (columns formed / differenced on the device), the count is
+    numpy's on that Jacobian, and several devices give the same bits."""
+    nc, R, N, T, eps = 96, 6, 512, 0.5, 1e-3
+    u = np.concatenate([0.2 + 0.7 * np.sin(np.linspace(0, np.pi, nc)) ** 2, np.linspace(0.0, 0.4, nc)])
+    cnt, J, lam, ms = _profile_stability(host, R, N, nc, T, u, eps, 1)
+    m = b200.EventDrivenMap([BETA], R, noNeurons=N)
+    m.SetTimeHorizon(T); m.SetProfileMode(nc)
+    Jp = m.ComputeDFDU(u, eps)
+    assert np.array_equal(J, Jp)
+    # the same Jacobian column by column through ComputeF (the callers' own loop, Stability.cpp:95-109)
+    f0 = m.ComputeF(u)
+    for i in (0, 7, nc, 2 * nc - 1):
+        du = u.copy(); du[i] += eps
+        assert np.array_equal(J[:, i], (m.ComputeF(du) - f0) * eps ** -1)
+    ref = np.linalg.eigvals(J + np.eye(2 * nc))
+    assert cnt == int(np.sum(np.abs(ref) > 1.0))
+    assert np.allclose(np.sort_complex(lam), np.sort_complex(ref), atol=1e-7)
+    ndev = b200.device_count()
+    if ndev >= 2:
+        cnt2, J2, lam2, ms2 = _profile_stability(host, R, N, nc, T, u, eps, min(ndev, 8))
+        assert cnt2 == cnt and np.array_equal(J2, J)

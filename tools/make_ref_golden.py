@@ -51,6 +51,8 @@ def case(tag, z, R, N, T=5.0, sigma=0.0, seed=42):
     cfg = O.edm_cfg(R=R, N=N, beta=BETA, sigma=sigma, seed=seed, precision=1, quirks=1, time_horizon=T,
                     beta_ext=(a["beta"].astype(np.float64) if sigma > 0 else None))
     fo, ao = O.edm_compute_f(cfg, z)
+    if not a["replay_equal"]:       # heterogeneous case: the ensemble fed to the oracle is the replay's
+        log(f"    oracle mean vs replay mean: {np.abs(ao['mean'] - a['mean_replay']).max():.3e}")
     log(f"    oracle f32+Q1: F={fo}  dF={np.abs(fo-f).max():.3e}  init_eq={np.array_equal(ao['init_index'], a['init_index'])} "
         f"last_eq={np.array_equal(ao['last_index'].T, a['last_index'])} crossed_eq={np.array_equal(ao['crossed_index'].T, a['crossed_index'])} "
         f"accept_eq={np.array_equal(ao['accept'], a['accept'])} "
@@ -69,6 +71,10 @@ case("C_offguess_1024", GUESS * np.array([1.01, 0.98, 1.03]), 8, 1024)
 case("D_sigma05_1024", GUESS, 16, 1024, sigma=0.5, seed=7)
 case("E_T2_768", GUESS, 5, 768, T=2.0)
 
+f1, a1 = REF.run(GUESS, BETA, 16, 1024, 5.0, 0.5, 7)
+f2, a2 = REF.run(GUESS, BETA, 16, 1024, 5.0, 0.5, 7)
+log(f"[sigma repeat] two fresh maps, same seed: F equal={np.array_equal(f1, f2)} beta(replay) equal={np.array_equal(a1['beta'], a2['beta'])} "
+    f"replay means equal={np.array_equal(a1['mean_replay'], a2['mean_replay'])}")
 t = time.time()
 flag, zs, hist, jac = REF.newton(GUESS, BETA, 1000, 1024)
 log(f"[newton N=1024 R=1000 tol=1e-4 eps=1e-2] {time.time()-t:.2f} s flag={flag} z*={zs} hist={hist}")
