@@ -163,33 +163,26 @@ __device__ __forceinline__ void ld_cell_keep(const double* p, double (&c)[4]) { 
 __device__ __forceinline__ void ld_cell_keep(const float* p, float (&c)[4]) { ld_keep_128(p, c, l2_policy_evict_last()); }
 
 // One query, split so that a thread can have several record gathers in flight: prepare() does the
-// bracket lookups and weights and names the record; finish() blends.  code: 0 regular, 1 xi NaN,
-// 2 xi out of range, 3 yi NaN, 4 yi out of range (same case analysis as interp2_point_s).
+// bracket lookups and weights and names the record; finish() blends (same case analysis as interp2_point_s:
+// two_pass_special / two_pass).
 template <typename T>
-struct BandPrep { uint32_t cell; int code; T wx, wy; };
+struct BandPrep { uint32_t cell; int fx, fy; T wx, wy; };
 
 template <typename T>
 __device__ __forceinline__ BandPrep<T> band_prepare(const AxisSmem<T>& X, const AxisSmem<T>& Y, T xq, T yq) {
   BandPrep<T> r;
-  r.cell = 0; r.wx = r.wy = (T)0;
   const BW<T> bx = bracket_weight_s<T>(X, xq);
-  if (bx.flag) { r.code = bx.flag == 2 ? 1 : 2; return r; }
-  r.wx = bx.w;
   const BW<T> by = bracket_weight_s<T>(Y, yq);
-  if (by.flag) { r.code = by.flag == 2 ? 3 : 4; return r; }
-  r.wy = by.w;
-  r.cell = (uint32_t)bx.a * (uint32_t)Y.n + (uint32_t)by.a;
-  r.code = 0;
+  r.fx = bx.flag; r.fy = by.flag;
+  r.wx = bx.w; r.wy = by.w;
+  r.cell = (bx.flag | by.flag) ? 0u : (uint32_t)bx.a * (uint32_t)Y.n + (uint32_t)by.a;
   return r;
 }
 template <typename T>
-__device__ __forceinline__ T band_finish(const BandPrep<T>& r, const T (&c)[4], T extrap) {
-  if (r.code == 1) return qnan<T>();
-  if (r.code == 2) return extrap;
-  const T v = r.code == 3 ? qnan<T>() : extrap;
-  const T ta = r.code ? v : blend(r.wy, c[0], c[1]);
-  const T tb = r.code ? v : blend(r.wy, c[2], c[3]);
-  return blend(r.wx, ta, tb);
+__device__ __forceinline__ T band_finish(int yfirst, const BandPrep<T>& r, const T (&c)[4], T extrap) {
+  T out;
+  if (two_pass_special<T>(yfirst, r.fx, r.fy, r.wx, r.wy, extrap, out)) return out;
+  return two_pass<T>(yfirst, r.wx, r.wy, c[0], c[1], c[2], c[3]);
 }
 
 constexpr int kBandCThreads = 256;
@@ -234,7 +227,7 @@ band_interp_kernel(Plan2Dev<T> p, BandDev bd, const uint16_t* __restrict__ seg, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t k = k0 + j * 32 + lane;
-        const T v = band_finish<T>(pr[j], q[j], extrap);
+        const T v = band_finish<T>(p.yfirst, pr[j], q[j], extrap);
         if (k < e1) __stcs(res + base + k, v);
       }
     }

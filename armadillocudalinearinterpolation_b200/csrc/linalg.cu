@@ -53,8 +53,20 @@ bool load_solver() {
   return s.ok = true;
 }
 
-struct Free { void* p = nullptr; bool host = false; ~Free() { if (p) { if (host) free(p); else cudaFree(p); } } };
 }  // namespace
+
+// cuSOLVER handle, parameters and buffers are kept per device between calls (creating a handle costs more than
+// a 1000 x 1000 GEEV); guarded by g_call.
+struct DevState {
+  int device = -1;
+  cusolverDnHandle_t hd = nullptr;
+  cusolverDnParams_t pr = nullptr;
+  void *dA = nullptr, *dW = nullptr, *dWork = nullptr, *hWork = nullptr;
+  int* dInfo = nullptr;
+  size_t capA = 0, capWork = 0, capHost = 0;
+};
+std::vector<DevState> g_states;
+std::mutex g_call;
 
 extern "C" int b200_eig_gen_f64(size_t n, const double* a_colmajor, double* w_re, double* w_im) {
   if (!a_colmajor || !w_re || !w_im) return fail(B200_ERR_INVALID_ARG, "eig_gen: NULL argument");
@@ -62,34 +74,54 @@ extern "C" int b200_eig_gen_f64(size_t n, const double* a_colmajor, double* w_re
   B200_TRY(require_device());
   if (!load_solver()) return fail(B200_ERR_UNSUPPORTED, "eig_gen: cuSOLVER (libcusolver.so.11 with cusolverDnXgeev) could not be loaded: %s", dlerror());
   Solver& s = g_solver;
-  cusolverDnHandle_t hd = nullptr;
-  cusolverDnParams_t pr = nullptr;
-  if (s.create(&hd) != CUSOLVER_STATUS_SUCCESS) return fail(B200_ERR_CUDA, "eig_gen: cusolverDnCreate failed");
-  struct Guard { Solver& s; cusolverDnHandle_t h; cusolverDnParams_t* p; ~Guard() { if (*p) s.destroy_params(*p); s.destroy(h); } } guard{s, hd, &pr};
-  if (s.create_params(&pr) != CUSOLVER_STATUS_SUCCESS) return fail(B200_ERR_CUDA, "eig_gen: cusolverDnCreateParams failed");
-  Free dA, dW, dWork, dInfo, hWork;
-  hWork.host = true;
-  B200_CUDA(cudaMalloc(&dA.p, n * n * sizeof(double)));
-  B200_CUDA(cudaMalloc(&dW.p, n * 2 * sizeof(double)));
-  B200_CUDA(cudaMalloc(&dInfo.p, sizeof(int)));
-  B200_CUDA(cudaMemcpy(dA.p, a_colmajor, n * n * sizeof(double), cudaMemcpyHostToDevice));
+  std::lock_guard<std::mutex> lk(g_call);
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  DevState* st = nullptr;
+  for (DevState& d : g_states) if (d.device == dev) st = &d;
+  if (!st) {
+    g_states.emplace_back();
+    st = &g_states.back();
+    st->device = dev;
+    if (s.create(&st->hd) != CUSOLVER_STATUS_SUCCESS || s.create_params(&st->pr) != CUSOLVER_STATUS_SUCCESS) {
+      g_states.pop_back();
+      return fail(B200_ERR_CUDA, "eig_gen: cusolverDnCreate failed");
+    }
+    B200_CUDA(cudaMalloc(&st->dInfo, sizeof(int)));
+  }
+  if (n * n > st->capA) {
+    cudaFree(st->dA); cudaFree(st->dW); st->dA = st->dW = nullptr; st->capA = 0;
+    B200_CUDA(cudaMalloc(&st->dA, n * n * sizeof(double)));
+    B200_CUDA(cudaMalloc(&st->dW, n * 2 * sizeof(double)));
+    st->capA = n * n;
+  }
+  B200_CUDA(cudaMemcpy(st->dA, a_colmajor, n * n * sizeof(double), cudaMemcpyHostToDevice));
   size_t wdev = 0, whost = 0;
-  cusolverStatus_t st = s.geev_size(hd, pr, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, (int64_t)n, CUDA_R_64F, dA.p,
-                                    (int64_t)n, CUDA_C_64F, dW.p, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F,
-                                    &wdev, &whost);
-  if (st != CUSOLVER_STATUS_SUCCESS) return fail(B200_ERR_CUDA, "eig_gen: cusolverDnXgeev_bufferSize status %d", (int)st);
-  B200_CUDA(cudaMalloc(&dWork.p, wdev ? wdev : 1));
-  hWork.p = malloc(whost ? whost : 1);
-  if (!hWork.p) return fail(B200_ERR_INVALID_ARG, "eig_gen: out of host memory");
-  st = s.geev(hd, pr, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, (int64_t)n, CUDA_R_64F, dA.p, (int64_t)n, CUDA_C_64F,
-              dW.p, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, dWork.p, wdev, hWork.p, whost, (int*)dInfo.p);
-  if (st != CUSOLVER_STATUS_SUCCESS) return fail(B200_ERR_CUDA, "eig_gen: cusolverDnXgeev status %d", (int)st);
+  cusolverStatus_t rc = s.geev_size(st->hd, st->pr, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, (int64_t)n, CUDA_R_64F,
+                                    st->dA, (int64_t)n, CUDA_C_64F, st->dW, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1,
+                                    CUDA_R_64F, &wdev, &whost);
+  if (rc != CUSOLVER_STATUS_SUCCESS) return fail(B200_ERR_CUDA, "eig_gen: cusolverDnXgeev_bufferSize status %d", (int)rc);
+  if (wdev > st->capWork) {
+    cudaFree(st->dWork); st->dWork = nullptr; st->capWork = 0;
+    B200_CUDA(cudaMalloc(&st->dWork, wdev));
+    st->capWork = wdev;
+  }
+  if (whost > st->capHost) {
+    free(st->hWork);
+    st->hWork = malloc(whost);
+    st->capHost = st->hWork ? whost : 0;
+    if (!st->hWork) return fail(B200_ERR_INVALID_ARG, "eig_gen: out of host memory");
+  }
+  rc = s.geev(st->hd, st->pr, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, (int64_t)n, CUDA_R_64F, st->dA, (int64_t)n,
+              CUDA_C_64F, st->dW, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, st->dWork, wdev, st->hWork, whost,
+              st->dInfo);
+  if (rc != CUSOLVER_STATUS_SUCCESS) return fail(B200_ERR_CUDA, "eig_gen: cusolverDnXgeev status %d", (int)rc);
   B200_CUDA(cudaDeviceSynchronize());
   int info = 0;
-  B200_CUDA(cudaMemcpy(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost));
+  B200_CUDA(cudaMemcpy(&info, st->dInfo, sizeof(int), cudaMemcpyDeviceToHost));
   if (info != 0) return fail(B200_ERR_CUDA, "eig_gen: cusolverDnXgeev info %d (QR iteration failed to converge)", info);
   std::vector<double> w(2 * n);
-  B200_CUDA(cudaMemcpy(w.data(), dW.p, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  B200_CUDA(cudaMemcpy(w.data(), st->dW, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < n; ++i) { w_re[i] = w[2 * i]; w_im[i] = w[2 * i + 1]; }
   return B200_OK;
 }

@@ -216,6 +216,7 @@ int b200_host_profile_stability(double beta, unsigned R, unsigned N, unsigned n_
     Stability st(Stability::ProblemType::equationFree, &map, &map);
     arma::mat J(n, n);
     map.ComputeDFDU(u, J);                                  // warm-up: allocations, NCCL channels
+    { arma::mat W(n, n, arma::fill::eye); arma::eig_gen(W); }   // ... and the eigen-solver's library / workspace
     auto t0 = std::chrono::steady_clock::now();
     const int unstable = st.ComputeNumUnstableEigenvalues(u);
     auto t1 = std::chrono::steady_clock::now();
@@ -235,7 +236,7 @@ int b200_host_profile_stability(double beta, unsigned R, unsigned N, unsigned n_
   } catch (const std::exception& e) { g_err = e.what(); return -1000; }
 }
 
-// arma::eig_gen as the host layer sees it (cuSOLVER behind the shim for n >= 128, own QR below / on request)
+// arma::eig_gen as the host layer sees it (cuSOLVER behind the shim for n >= 256, own QR below / on request)
 int b200_host_eig_gen(int n, const double* A_colmajor, double* eig_re, double* eig_im, double* ms_out) {
   try {
     arma::mat A(n, n);

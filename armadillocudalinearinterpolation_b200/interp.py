@@ -100,7 +100,7 @@ class Interp2Plan:
     """Grid (X, Y, Z) resident in HBM.  Z is Y.size x X.size (rows follow Y), any memory order;
     it is stored column-major like arma::mat."""
 
-    NO_CELLS, FORCE_CELLS, NO_BANDS, FORCE_BANDS, NO_TILES, FORCE_TILES = 1, 2, 4, 8, 16, 32   # include/b200_interp.h layout flags
+    NO_CELLS, FORCE_CELLS, NO_BANDS, FORCE_BANDS, NO_TILES, FORCE_TILES, ORDER_YX = 1, 2, 4, 8, 16, 32, 64   # include/b200_interp.h flags
 
     def __init__(self, X, Y, Z, flags=0):
         X = _np(X)

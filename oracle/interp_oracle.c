@@ -6,6 +6,10 @@
 #include <stdint.h>
 #include "oracle.h"
 
+/* pass order of interp2 (see two_pass in the .inc): 0 = along X then Y (default), 1 = along Y then X */
+static int oracle_interp2_yfirst = 0;
+void oracle_interp2_set_order(int y_first) { oracle_interp2_yfirst = y_first ? 1 : 0; }
+
 #define REAL double
 #define SUFFIX(name) name##_f64
 #define REAL_NAN ((double)NAN)

@@ -42,9 +42,12 @@ int oracle_interp1_f32(const float* xg, const float* yg, size_t ng, const float*
                        size_t ni, float* yi, int32_t* idx_out, float extrap, int scan,
                        int nthreads);
 
-/* arma::interp2(X,Y,Z,XI,YI,ZI,"linear",extrap) — two separable passes of the interp1
- * rule (first along Y on every column of Z, then along X), fn_interp2.hpp.
+/* arma::interp2(X,Y,Z,XI,YI,ZI,"linear",extrap) — two separable passes of the interp1 rule, fn_interp2.hpp.
+ * Order: along X first (whole columns of Z), then along Y — as recalled by two independent readers of
+ * fn_interp2.hpp; UNVERIFIED (Armadillo is absent).  oracle_interp2_set_order(1) selects the mirrored order
+ * (along Y, then X), matching the product's B200_INTERP2_ORDER_YX flag.
  * z: ny x nx column-major; zi: nyi x nxi column-major. */
+void oracle_interp2_set_order(int y_first);
 int oracle_interp2_grid_f64(const double* x, size_t nx, const double* y, size_t ny,
                             const double* z, const double* xi, size_t nxi,
                             const double* yi, size_t nyi, double* zi, double extrap,

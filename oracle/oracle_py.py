@@ -76,8 +76,13 @@ def interp1(xg, yg, xi, extrap=np.nan, scan=False, nthreads=1, want_idx=True):
     return (yi, idx) if want_idx else yi
 
 
-def interp2_grid(x, y, z, xi, yi, extrap=np.nan, nthreads=1):
-    """z: (ny, nx) array (any memory order) -> zi (nyi, nxi)."""
+def _order(y_first):
+    lib().oracle_interp2_set_order(int(bool(y_first)))
+
+
+def interp2_grid(x, y, z, xi, yi, extrap=np.nan, nthreads=1, y_first=False):
+    """z: (ny, nx) array (any memory order) -> zi (nyi, nxi).  y_first: the mirrored pass order."""
+    _order(y_first)
     dt, sfx, creal = _real(z.dtype)
     x = np.ascontiguousarray(x, dt); y = np.ascontiguousarray(y, dt)
     xi = np.ascontiguousarray(xi, dt); yi = np.ascontiguousarray(yi, dt)
@@ -93,7 +98,8 @@ def interp2_grid(x, y, z, xi, yi, extrap=np.nan, nthreads=1):
     return zi
 
 
-def interp2_scattered(x, y, z, xq, yq, extrap=np.nan, nthreads=1):
+def interp2_scattered(x, y, z, xq, yq, extrap=np.nan, nthreads=1, y_first=False):
+    _order(y_first)
     dt, sfx, creal = _real(z.dtype)
     x = np.ascontiguousarray(x, dt); y = np.ascontiguousarray(y, dt)
     xq = np.ascontiguousarray(xq, dt); yq = np.ascontiguousarray(yq, dt)

@@ -53,6 +53,11 @@ def interp_cases():
         yq = rng.uniform(-1.1, 1.1, 400).astype(dt)
         xq[:4] = [x[0], x[-1], np.nan, x[3]]
         yq[:4] = [y[0], y[-1], 0.0, np.nan]
+        # corner cases that tell the two pass orders apart (finite extrap): NaN in one coordinate and out of
+        # range in the other -> the LAST pass decides; out of range in the first-pass coordinate only -> the
+        # second pass blends extrap with itself
+        xq[4:10] = [np.nan, x[0] - 1, x[0] - 1, x[5], np.nan, x[-1] + 1]
+        yq[4:10] = [y[0] - 1, np.nan, 0.3, y[-1] + 1, y[-1] + 1, y[0] - 1]
         xi = rng.uniform(x[0] - 0.05, x[-1] + 0.05, 23).astype(dt)
         yi = rng.uniform(-1.1, 1.1, 31).astype(dt)
         out[f"i2_{tag}_x"] = x
@@ -60,10 +65,16 @@ def interp_cases():
         out[f"i2_{tag}_z"] = z
         out[f"i2_{tag}_xq"] = xq
         out[f"i2_{tag}_yq"] = yq
-        out[f"i2_{tag}_zq"] = O.interp2_scattered(x, y, z, xq, yq, extrap=3.5)
+        xi[:3] = [np.nan, x[0] - 1, x[2]]
+        yi[:3] = [y[0] - 1, np.nan, y[4]]
+        out[f"i2_{tag}_zq"] = O.interp2_scattered(x, y, z, xq, yq, extrap=3.5)              # default order: X then Y
+        out[f"i2_{tag}_zq_yx"] = O.interp2_scattered(x, y, z, xq, yq, extrap=3.5, y_first=True)
         out[f"i2_{tag}_xi"] = xi
         out[f"i2_{tag}_yi"] = yi
         out[f"i2_{tag}_zi"] = np.ascontiguousarray(O.interp2_grid(x, y, z, xi, yi, extrap=np.nan))
+        out[f"i2_{tag}_zi_yx"] = np.ascontiguousarray(O.interp2_grid(x, y, z, xi, yi, extrap=np.nan, y_first=True))
+        out[f"i2_{tag}_zi_e"] = np.ascontiguousarray(O.interp2_grid(x, y, z, xi, yi, extrap=3.5))
+        out[f"i2_{tag}_zi_e_yx"] = np.ascontiguousarray(O.interp2_grid(x, y, z, xi, yi, extrap=3.5, y_first=True))
     return out
 
 

@@ -25,12 +25,32 @@ def test_interp1_golden(b200, tag, kind):
 
 
 @pytest.mark.parametrize("tag", ["f64", "f32"])
-def test_interp2_golden(b200, tag):
+@pytest.mark.parametrize("y_first", [False, True])
+def test_interp2_golden(b200, tag, y_first):
+    """Both orders of Armadillo's two separable passes (default: along X, then Y; B200_INTERP2_ORDER_YX: the
+    mirrored order), every layout of the scattered path and the tensor-grid kernel, including the corner cases
+    that tell the orders apart: NaN in one coordinate with the other out of range (the LAST pass decides) and a
+    finite extrap value blended with itself by the second pass."""
     g = lambda k: GOLD[f"i2_{tag}_{k}"]
-    plan = b200.Interp2Plan(g("x"), g("y"), g("z"))
-    assert same_bits(plan.scattered(g("xq"), g("yq"), extrap=3.5), g("zq"))
-    assert same_bits(plan.grid(g("xi"), g("yi")), g("zi"))
-    assert same_bits(b200.interp2(g("x"), g("y"), g("z"), g("xi"), g("yi")), g("zi"))
+    sfx = "_yx" if y_first else ""
+    P = b200.Interp2Plan
+    order = P.ORDER_YX if y_first else 0
+    for layout in (0, P.FORCE_CELLS, P.FORCE_TILES, P.NO_CELLS | P.NO_TILES, P.FORCE_CELLS | P.FORCE_BANDS):
+        plan = P(g("x"), g("y"), g("z"), flags=order | layout)
+        assert same_bits(plan.scattered(g("xq"), g("yq"), extrap=3.5), g("zq" + sfx)), layout
+        if layout & P.FORCE_BANDS:     # the banded pipeline serves device buffers
+            import torch
+            zq = plan.scattered(torch.from_numpy(g("xq")).cuda(), torch.from_numpy(g("yq")).cuda(), extrap=3.5)
+            torch.cuda.synchronize()
+            assert same_bits(zq.cpu().numpy(), g("zq" + sfx))
+        assert same_bits(plan.grid(g("xi"), g("yi")), g("zi" + sfx))
+        assert same_bits(plan.grid(g("xi"), g("yi"), extrap=3.5), g("zi_e" + sfx))
+    if not y_first:
+        assert same_bits(b200.interp2(g("x"), g("y"), g("z"), g("xi"), g("yi")), g("zi"))
+    # the two orders agree to rounding wherever both are finite
+    a, b = g("zq"), g("zq_yx")
+    ok = ~np.isnan(a) & ~np.isnan(b)
+    assert np.max(np.abs(a[ok] - b[ok])) <= 4 * np.finfo(a.dtype).eps * max(1.0, np.max(np.abs(a[ok])))
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])

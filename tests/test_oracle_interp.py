@@ -25,10 +25,33 @@ def test_interp1_golden(oracle, tag, kind):
 @pytest.mark.parametrize("tag", ["f64", "f32"])
 def test_interp2_golden(oracle, tag):
     g = lambda k: GOLD[f"i2_{tag}_{k}"]
-    zq = oracle.interp2_scattered(g("x"), g("y"), g("z"), g("xq"), g("yq"), extrap=3.5)
-    assert same_bits(zq, g("zq"))
-    zi = oracle.interp2_grid(g("x"), g("y"), g("z"), g("xi"), g("yi"))
-    assert same_bits(zi, g("zi"))
+    for y_first, sfx in ((False, ""), (True, "_yx")):
+        zq = oracle.interp2_scattered(g("x"), g("y"), g("z"), g("xq"), g("yq"), extrap=3.5, y_first=y_first)
+        assert same_bits(zq, g("zq" + sfx))
+        zi = oracle.interp2_grid(g("x"), g("y"), g("z"), g("xi"), g("yi"), y_first=y_first)
+        assert same_bits(zi, g("zi" + sfx))
+        # the grid API and the per-point restatement are the same two passes
+        zi_e = oracle.interp2_grid(g("x"), g("y"), g("z"), g("xi"), g("yi"), extrap=3.5, y_first=y_first)
+        assert same_bits(zi_e, g("zi_e" + sfx))
+        per_point = oracle.interp2_scattered(g("x"), g("y"), g("z"), np.repeat(g("xi"), g("yi").size),
+                                             np.tile(g("yi"), g("xi").size), extrap=3.5, y_first=y_first)
+        assert same_bits(per_point.reshape(g("xi").size, g("yi").size).T, zi_e)
+
+
+def test_interp2_pass_order_corner_cases(oracle):
+    """What distinguishes the two orders (SURVEY 8c / round-1 advisor finding): the LAST pass decides special
+    values.  Default order = along X, then Y (as Armadillo's fn_interp2.hpp is recalled: unverified)."""
+    x = np.array([0.0, 1.0, 2.0]); y = np.array([0.0, 1.0]); z = np.array([[1.0, 2.0, 4.0], [3.0, 5.0, 9.0]])
+    e = 7.5
+    q = lambda xq, yq, yf: oracle.interp2_scattered(x, y, z, np.array([xq]), np.array([yq]), extrap=e, y_first=yf)[0]
+    assert q(0.5, 0.5, False) == q(0.5, 0.5, True) == 2.75
+    assert q(np.nan, 5.0, False) == e and np.isnan(q(np.nan, 5.0, True))        # xi NaN, yi out of range
+    assert np.isnan(q(5.0, np.nan, False)) and q(5.0, np.nan, True) == e        # xi out of range, yi NaN
+    assert q(5.0, 0.25, False) == (1 - 0.25) * e + 0.25 * e and q(5.0, 0.25, True) == e
+    assert q(0.5, 5.0, False) == e and q(0.5, 5.0, True) == (1 - 0.5) * e + 0.5 * e
+    inf = np.inf                                                                 # extrap = inf blended with weight 0
+    r = oracle.interp2_scattered(x, y, z, np.array([5.0]), np.array([0.0]), extrap=inf)[0]
+    assert np.isnan(r)                                                           # (1-0)*inf + 0*inf, literally
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
