@@ -458,7 +458,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       if (HET) {
         bt[q] = A.beta[(size_t)r * N + j];
         ibm1[q] = one / (bt[q] - one);
-        filt[q] = bt[q] >= (T)1.5;
+        filt[q] = bt[q] >= (T)1.5 && (k.vth - k.I) > (T)0;
       }
     } else {
       v[q] = (T)0; s[q] = (T)0;
@@ -469,7 +469,9 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   const T hb = A.beta_mean;
   const T h_ibm1 = one / (hb - one);
   const T h_i1mb = one / (one - hb);
-  const bool h_filt = hb >= (T)1.5;
+  // the conservative filter assumes vth - I > 0 and beta > 1 (g decreasing in p); outside that regime every
+  // neuron is handed to the exact predicate instead (advisor finding, round 1)
+  const bool h_filt = hb >= (T)1.5 && (k.vth - k.I) > (T)0;
   const float h_invb32 = (float)(one / hb);
   const T inv_vmI = one / (k.vth - k.I);
   const T vmI = k.vth - k.I;
@@ -511,7 +513,9 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
         // operations; whole warps far from the fronts leave here without touching the MUFU path
         const T d1 = v[q] - k.vth;
         const T g_ub = (rr >= one) ? d1 + (s[q] - vmI) * (HET ? ibm1[q] : h_ibm1) : (d1 - s[q]) + vmI;
-        if (g_ub < (T)-1e-9) maybe = false;
+        // margin above the rounding of g_ub's own terms in the run's arithmetic (FP32: ~1e-7 relative)
+        const T m1 = sizeof(T) == 4 ? (T)1e-5 * (one + fabs(d1) + fabs(s[q])) : (T)1e-9;
+        if (g_ub < -m1) maybe = false;
         else if (rr > (T)1e-30 && rr < (T)1e30) {
           const float p32 = exp2f(__log2f((float)rr) * (HET ? (float)(one / b) : h_invb32));
           const T p = (T)p32;

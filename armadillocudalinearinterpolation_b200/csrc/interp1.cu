@@ -22,6 +22,7 @@
 //    operation individually rounded (__dmul_rn, ...), bit-identical to the CPU oracle.
 #include <cstdlib>
 #include "interp_common.cuh"
+#include "host_staging.cuh"
 
 namespace b200 {
 namespace {
@@ -173,6 +174,7 @@ struct b200_interp1_plan {
   void* st_out[2] = {nullptr, nullptr};
   int32_t* st_idx[2] = {nullptr, nullptr};
   size_t st_cap = 0;  // queries per slot
+  StagePool pool;     // pinned ring for pageable host buffers
   cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
@@ -290,6 +292,14 @@ int plan1_ensure_staging(b200_interp1_plan* p, size_t ni, bool want_idx) {
 template <typename T>
 int plan1_exec_host(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* idx, T extrap) {
   if (ni == 0) return B200_OK;
+  if (ni >= ((size_t)1 << 21) && (host_pageable(xi) || host_pageable(yi) || host_pageable(idx))) {
+    // ordinary (pageable) arma::vec memory: pinned ring + copier threads (host_staging.cuh), same kernels
+    std::vector<StageArray> arrays = {{xi, nullptr, sizeof(T)}, {nullptr, yi, sizeof(T)}};
+    if (idx) arrays.push_back({nullptr, idx, sizeof(int32_t)});
+    return staged_run(p->pool, p->device, arrays, ni, [&](const std::vector<void*>& d, size_t n, cudaStream_t st) {
+      return plan1_launch<T>(p, (const T*)d[0], n, (T*)d[1], idx ? (int32_t*)d[2] : nullptr, extrap, st);
+    });
+  }
   B200_TRY(plan1_ensure_staging<T>(p, ni, idx != nullptr));
   const size_t cap = p->st_cap;
   int slot = 0;

@@ -224,3 +224,42 @@ def test_in_process_multi_device_is_bitwise_single_device(b200):
     assert np.array_equal(Ja, Jb) and np.array_equal(fa, fb)
     uc = np.stack([u * (1 + 1e-3 * k) for k in range(40)], axis=1)
     assert np.array_equal(a.ComputeFBatch(uc), b.ComputeFBatch(uc))
+
+
+def test_drive_above_threshold_bypasses_the_candidate_filter(b200, oracle):
+    """The two-stage candidate filter assumes vth - I > 0 (round-1 advisor finding): with the drive at or above
+    threshold every neuron is handed to the exact predicate instead, and the event sequence is still the oracle's."""
+    for I in (1.0, 1.2):
+        cfg = dict(R=2, N=256, I=I, time_horizon=0.3)
+        m = make_map(b200, cfg)
+        f = m.ComputeF(Z_DRIVER)
+        fo, a = oracle.edm_compute_f(oracle.edm_cfg(**cfg), Z_DRIVER)
+        assert np.array_equal(m.DebugFetch("event_count")[0], a["event_count"])
+        assert np.array_equal(m.DebugFetch("last_index")[0], a["last_index"])
+        assert np.array_equal(np.isfinite(f), np.isfinite(fo))
+        ok = np.isfinite(fo)
+        assert np.max(np.abs(f[ok] - fo[ok]), initial=0.0) < 1e-9
+
+
+def test_repeated_evaluations_are_bitwise_identical(b200):
+    """compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer.md), so the race check is empirical:
+    the evolve kernel's double-buffered candidate list, its one-event-late bookkeeping and the speculative event
+    must give the same bits on every run — 40 evaluations of a heterogeneous ensemble at three launch shapes, front
+    and profile map, every per-item output compared."""
+    for N, prof in ((512, 0), (1024, 0), (2048, 0), (512, 48)):
+        m = make_map(b200, dict(R=24, N=N, sigma=0.4, seed=11))
+        if prof:
+            m.SetTimeHorizon(0.7); m.SetProfileMode(prof)
+            u = np.concatenate([0.2 + 0.7 * np.sin(np.linspace(0, np.pi, prof)) ** 2, np.linspace(0.0, 0.4, prof)])
+        else:
+            u = Z_DRIVER
+        ref = None
+        for rep in range(40):
+            f = m.ComputeF(u)
+            got = [f, m.DebugFetch("position"), m.DebugFetch("event_count"), m.DebugFetch("accept")]
+            if not prof:
+                got += [m.DebugFetch("last_index"), m.DebugFetch("crossed_time")]
+            if ref is None:
+                ref = got
+            else:
+                assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(ref, got)), (N, prof, rep)

@@ -62,3 +62,14 @@ open(f"profiles/{tag}_launch_list.md", "w").write("\n".join(L) + "\n")
 import shutil
 shutil.copy(launches, f"profiles/{tag}_launches.csv")
 print(json.dumps(traffic, indent=1))
+# roofline_traffic.json: the figure bench.py reports as roofline.traffic, stamped with a hash of the kernel sources it
+# was captured for (bench.py flags it STALE when the sources have changed since)
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+key = [k for k in traffic if "interp2_scattered_smem_kernel<double, 2>" in k]
+if key:
+    json.dump({"interp2_scattered_f64": {"dram_bytes_per_launch": int(traffic[key[0]]),
+                                         "source_sha1": bench.source_stamp(bench.INTERP2_SOURCES), "capture": tag,
+                                         "source": f"profiles/{tag}_ncu_hot_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch, 1e8 queries, tile layout)"}},
+              open("profiles/roofline_traffic.json", "w"), indent=1)

@@ -1,6 +1,7 @@
 """Small driver for ncu: one launch (after warm-up) of each hot kernel at bench sizes."""
 import sys
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import armadillocudalinearinterpolation_b200 as B
 import bench
