@@ -1,6 +1,6 @@
 """A/B of two builds of the library on the map kernel: python tools/edm_ab.py <lib.so>."""
 import sys, time
-sys.path.insert(0, "/root/repo")
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from armadillocudalinearinterpolation_b200 import _lib
 if len(sys.argv) > 1:

@@ -4,9 +4,12 @@
 """
 import collections, csv, json, sys
 raw, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
-rows = list(csv.reader(open(raw)))
-hdr, units, data = rows[0], rows[1], rows[2:]
-idx = {h: i for i, h in enumerate(hdr)}
+# `raw` may be a comma-separated list of exports (one per capture); columns differ between captures
+captures = []
+for path in raw.split(","):
+    rows = list(csv.reader(open(path)))
+    if len(rows) > 2:
+        captures.append((rows[0], rows[1], rows[2:]))
 M = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
      ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM % peak"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
      ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "LSU wavefronts % peak"),
@@ -15,16 +18,18 @@ M = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "DRAM read"), 
      ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"), ("launch__registers_per_thread", "regs/thread"),
      ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("smsp__inst_executed.sum", "warp instructions")]
 seen = collections.OrderedDict()
-for r in data:
-    name = r[idx["Kernel Name"]]
-    seen.setdefault(name, []).append(r)
+for hdr, units, data in captures:
+    idx = {h: i for i, h in enumerate(hdr)}
+    for r in data:
+        name = r[idx["Kernel Name"]]
+        seen.setdefault(name, []).append((r, idx, units))
 out = [f"# ncu --set full summary ({tag})", "",
        "Captured with `ncu --set full --clock-control none --import-source on` on one B200 (one launch per",
        "row: the LAST captured launch of each kernel, i.e. after warm-up launches of the same process).",
        "Times under ncu are serialised and cold-cache; bench.py's CUDA-event numbers are the ones reported.", ""]
 traffic = {}
 for name, rs in seen.items():
-    r = rs[-1]
+    r, idx, units = rs[-1]
     short = name.replace("void b200::<unnamed>::", "").replace("b200::<unnamed>::", "")[:110]
     out += [f"## `{short}`", "", "| metric | value |", "|---|---|"]
     for m, label in M:
