@@ -6,11 +6,22 @@
 // status code plus a thread-local message (b200_last_error()).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stddef.h>
 #include <stdint.h>
 #include "b200_common.h"
 
 namespace b200 {
+
+// NVTX range (header-only NVTX3: a no-op unless a profiler is attached) around host-side phases: the map's
+// lift / evolve / reduce / all-gather (edm.cu) and the slots of the host-buffer pipelines (interp1.cu, interp2.cu,
+// host_staging.cuh)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 int fail(int status, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);

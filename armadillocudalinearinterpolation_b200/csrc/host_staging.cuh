@@ -109,6 +109,7 @@ int staged_run(StagePool& pool, int device, const std::vector<StageArray>& array
       for (size_t c = (size_t)t; c < nchunks; c += (size_t)nworkers, slot ^= 1) {
         const size_t off = c * kChunkElems, cnt = n - off < kChunkElems ? n - off : kChunkElems;
         B200_TRY(drain(slot));
+        NvtxRange nvtx_chunk("staged:chunk memcpy+h2d+kernel+d2h");
         for (size_t a = 0; a < arrays.size(); ++a)
           if (arrays[a].in) {
             memcpy(w.pin[slot][a], (const char*)arrays[a].in + off * arrays[a].elem, cnt * arrays[a].elem);

@@ -32,15 +32,80 @@ template <typename T> struct Loader1;
 template <> struct Loader1<double> { using type = LoadSeg1D; };
 template <> struct Loader1<float> { using type = LoadSeg1F; };
 
+// ---- non-uniform knots: one record per uniform bin (round 2; opt-in, see plan1_create for the measurement) ----
+// The general path costs two DEPENDENT gathers per query (first2[bin], then the segment record, then more
+// records while scanning forward).  A bin record holds everything a query of that bin normally needs in ONE
+// line: a0 = the last knot before the bin, the number of knots inside the bin, and knots / values a0, a0+1, a0+2
+// (clamped at the last knot).  A query resolves from the record alone unless its bracket starts at a0+2 or later
+// (bins holding >= 2 knots below the query), in which case it continues with the segment records as before.
+// 64 bytes per bin for double, 32 for float; the bracket is still fixed by comparing against stored knots.
+template <typename T>
+struct alignas(sizeof(T) == 8 ? 64 : 32) BinRec {
+  int32_t a0, cnt;
+  T x[3], y[3];
+};
+
+template <typename T>
+__global__ void build_binrec_kernel(const T* __restrict__ x, const T* __restrict__ y, const int32_t* __restrict__ first,
+                                    int n, int nb, BinRec<T>* __restrict__ rec) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nb) return;
+  BinRec<T> r;
+  r.a0 = max(first[k] - 1, 0);
+  r.cnt = first[k + 1] - first[k];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { const int j = min(r.a0 + i, n - 1); r.x[i] = x[j]; r.y[i] = y[j]; }
+  rec[k] = r;
+}
+
+__device__ __forceinline__ BinRec<double> ld_binrec(const BinRec<double>* p) {
+  double a[4], b[4];
+  ld_keep_256(reinterpret_cast<const double*>(p), a);
+  ld_keep_256(reinterpret_cast<const double*>(p) + 4, b);
+  BinRec<double> r;
+  const long long bits = __double_as_longlong(a[0]);
+  r.a0 = (int32_t)(bits & 0xffffffffll); r.cnt = (int32_t)(bits >> 32);
+  r.x[0] = a[1]; r.x[1] = a[2]; r.x[2] = a[3]; r.y[0] = b[0]; r.y[1] = b[1]; r.y[2] = b[2];
+  return r;
+}
+__device__ __forceinline__ BinRec<float> ld_binrec(const BinRec<float>* p) {
+  float a[4], b[4];
+  const uint64_t pol = l2_policy_evict_last();
+  ld_keep_128(reinterpret_cast<const float*>(p), a, pol);
+  ld_keep_128(reinterpret_cast<const float*>(p) + 4, b, pol);
+  BinRec<float> r;
+  r.a0 = __float_as_int(a[0]); r.cnt = __float_as_int(a[1]);
+  r.x[0] = a[2]; r.x[1] = a[3]; r.x[2] = b[0]; r.y[0] = b[1]; r.y[1] = b[2]; r.y[2] = b[3];
+  return r;
+}
+
 template <typename T>
 __device__ __forceinline__ T interp1_one(const AxisDev<T>& ax, const typename Loader1<T>::type& ld,
-                                         T q, T extrap, int32_t& idx) {
+                                         const BinRec<T>* __restrict__ rec, T q, T extrap, int32_t& idx) {
   if (!(q >= ax.x0 && q <= ax.xmax)) {  // out of range -> extrap_val; NaN query -> NaN
     idx = -1;
     return (q != q) ? qnan<T>() : extrap;
   }
   Seg1<T> sg;
-  idx = find_bracket(ax, ld, q, sg);
+  if (rec) {
+    const BinRec<T> r = ld_binrec(rec + bin_of(ax, q));
+    const bool up1 = (r.a0 + 1 < ax.n) && (r.x[1] <= q);
+    const bool up2 = (r.a0 + 2 < ax.n) && (r.x[2] <= q);
+    if (!up2) {   // the bracket is a0 or a0 + 1: everything is in the record
+      idx = r.a0 + (up1 ? 1 : 0);
+      sg.xa = up1 ? r.x[1] : r.x[0]; sg.xb = up1 ? r.x[2] : r.x[1];
+      sg.ya = up1 ? r.y[1] : r.y[0]; sg.yb = up1 ? r.y[2] : r.y[1];
+    } else if (r.cnt > kLinearScanMax) {
+      idx = find_bracket(ax, ld, q, sg);   // clustered knots: the bounded binary search of the table path
+    } else {
+      int a = r.a0 + 2;
+      sg = ld(a);
+      while (sg.xb <= q && a + 1 < ax.n) { a += 1; sg = ld(a); }
+      idx = a;
+    }
+  } else {
+    idx = find_bracket(ax, ld, q, sg);
+  }
   return blend(weight_of(sg.xa, sg.xb, q), sg.ya, sg.yb);
 }
 
@@ -55,8 +120,8 @@ template <> __device__ __forceinline__ LoadSeg1F make_loader1<float>(const float
 // of this kernel at 1e7 and 1e8 queries — the gather RATE bounds it, not the bytes — and not kept.)
 template <typename T, bool WANT_IDX>
 __global__ void __launch_bounds__(kThreads)
-interp1_vec_kernel(AxisDev<T> ax, const T* __restrict__ seg, const T* __restrict__ xi,
-                   T* __restrict__ yi, int32_t* __restrict__ idx, size_t nvec, T extrap) {
+interp1_vec_kernel(AxisDev<T> ax, const T* __restrict__ seg, const BinRec<T>* __restrict__ rec,
+                   const T* __restrict__ xi, T* __restrict__ yi, int32_t* __restrict__ idx, size_t nvec, T extrap) {
   constexpr int V = Vec256<T>::n;
   const auto ld = make_loader1<T>(seg);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -65,7 +130,7 @@ interp1_vec_kernel(AxisDev<T> ax, const T* __restrict__ seg, const T* __restrict
     int32_t id[V];
     ld_stream_256(xi + i * V, q);
 #pragma unroll
-    for (int j = 0; j < V; ++j) y[j] = interp1_one<T>(ax, ld, q[j], extrap, id[j]);
+    for (int j = 0; j < V; ++j) y[j] = interp1_one<T>(ax, ld, rec, q[j], extrap, id[j]);
     st_stream_256(yi + i * V, y);
     if (WANT_IDX) {
       if (V == 8) {
@@ -80,14 +145,14 @@ interp1_vec_kernel(AxisDev<T> ax, const T* __restrict__ seg, const T* __restrict
 // Scalar kernel: tails and unaligned buffers.
 template <typename T, bool WANT_IDX>
 __global__ void __launch_bounds__(kThreads)
-interp1_scalar_kernel(AxisDev<T> ax, const T* __restrict__ seg, const T* __restrict__ xi,
-                      T* __restrict__ yi, int32_t* __restrict__ idx, size_t begin, size_t end,
-                      T extrap) {
+interp1_scalar_kernel(AxisDev<T> ax, const T* __restrict__ seg, const BinRec<T>* __restrict__ rec,
+                      const T* __restrict__ xi, T* __restrict__ yi, int32_t* __restrict__ idx, size_t begin,
+                      size_t end, T extrap) {
   const auto ld = make_loader1<T>(seg);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
     int32_t id;
-    yi[i] = interp1_one<T>(ax, ld, xi[i], extrap, id);
+    yi[i] = interp1_one<T>(ax, ld, rec, xi[i], extrap, id);
     if (WANT_IDX) idx[i] = id;
   }
 }
@@ -167,6 +232,7 @@ struct b200_interp1_plan {
   Axis<float> ax32;
   void* yg = nullptr;   // device copy of the values
   void* seg = nullptr;  // [ng][4] segment records
+  void* binrec = nullptr;  // [nb] bin records (non-uniform knots), or nullptr
   size_t smem_bytes = 0;  // > 0: the grid fits the shared-memory path
   cudaStream_t stream[2] = {nullptr, nullptr};
   // staging for host-buffer execution (allocated on first use)
@@ -189,6 +255,11 @@ int plan1_build_seg(b200_interp1_plan* p, cudaStream_t st) {
   Axis<T>& A = axis_of<T>(p);
   build_seg1_kernel<T><<<grid_for(p->ng), kThreads, 0, B200_CNT(st)>>>(A.x, (const T*)p->yg, (int)p->ng,
                                                              (T*)p->seg);
+  if (p->binrec) {
+    const AxisDev<T>& d = A.dev;
+    build_binrec_kernel<T><<<grid_for((size_t)d.nb), kThreads, 0, B200_CNT(st)>>>(A.x, (const T*)p->yg, d.first, d.n, d.nb,
+                                                                                (BinRec<T>*)p->binrec);
+  }
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -204,6 +275,16 @@ int plan1_create(b200_interp1_plan* p, const T* xg, const T* yg, size_t ng) {
   B200_CUDA(cudaMemsetAsync(p->yg, 0, ng * sizeof(T) + 16, p->stream[0]));
   B200_CUDA(cudaMalloc(&p->seg, ng * 4 * sizeof(T)));
   B200_CUDA(cudaMemcpyAsync(p->yg, yg, ng * sizeof(T), cudaMemcpyHostToDevice, p->stream[0]));
+  {
+    // bin records for non-uniform knots: OPT-IN (B200_INTERP1_BINREC=1).  Measured at 1e6 knots x 1e7 queries
+    // (tools/interp1_cfg1_sweep.py): unsorted 110 -> 101 us, sorted 53 -> 56 us — a random gather costs one LSU
+    // wavefront per lane per load instruction, so one 64-byte record (two 256-bit loads) is no cheaper than the
+    // 8-byte bucket entry + 32-byte segment record it replaces, and the table doubles (64 MB).
+    const AxisDev<T>& d = axis_of<T>(p).dev;
+    const char* e = getenv("B200_INTERP1_BINREC");
+    if (d.mode == 1 && (size_t)d.nb * sizeof(BinRec<T>) <= ((size_t)96 << 20) && (e && e[0] == '1'))
+      B200_CUDA(cudaMalloc(&p->binrec, (size_t)d.nb * sizeof(BinRec<T>)));
+  }
   B200_TRY(plan1_build_seg<T>(p, p->stream[0]));
   B200_CUDA(cudaStreamSynchronize(p->stream[0]));
   {
@@ -249,16 +330,18 @@ int plan1_launch(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* i
     static const size_t forced = [] { const char* e = getenv("B200_INTERP1_GRID_MULT"); return (size_t)(e && atoi(e) > 0 ? atoi(e) : 0); }();
     const size_t mult = forced ? forced : (blocks > (size_t)148 * 256 ? 64 : 16);
     int grid = (int)(blocks < (size_t)148 * mult ? blocks : (size_t)148 * mult);
-    if (idx) interp1_vec_kernel<T, true><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, xi, yi, idx, nvec, extrap);
-    else interp1_vec_kernel<T, false><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, xi, yi, nullptr, nvec, extrap);
+    const BinRec<T>* rec = (const BinRec<T>*)p->binrec;
+    if (idx) interp1_vec_kernel<T, true><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, rec, xi, yi, idx, nvec, extrap);
+    else interp1_vec_kernel<T, false><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, rec, xi, yi, nullptr, nvec, extrap);
   }
   size_t done = nvec * V;
   if (done < ni) {
     size_t rem = ni - done;
     size_t blocks = (rem + kThreads - 1) / kThreads;
     int grid = (int)(blocks < (size_t)148 * 64 ? blocks : (size_t)148 * 64);
-    if (idx) interp1_scalar_kernel<T, true><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, xi, yi, idx, done, ni, extrap);
-    else interp1_scalar_kernel<T, false><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, xi, yi, nullptr, done, ni, extrap);
+    const BinRec<T>* rec = (const BinRec<T>*)p->binrec;
+    if (idx) interp1_scalar_kernel<T, true><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, rec, xi, yi, idx, done, ni, extrap);
+    else interp1_scalar_kernel<T, false><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, rec, xi, yi, nullptr, done, ni, extrap);
   }
   B200_CUDA(cudaGetLastError());
   return B200_OK;
@@ -292,6 +375,7 @@ int plan1_ensure_staging(b200_interp1_plan* p, size_t ni, bool want_idx) {
 template <typename T>
 int plan1_exec_host(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* idx, T extrap) {
   if (ni == 0) return B200_OK;
+  NvtxRange nvtx_call("interp1:exec_host");
   if (ni >= ((size_t)1 << 21) && (host_pageable(xi) || host_pageable(yi) || host_pageable(idx))) {
     // ordinary (pageable) arma::vec memory: pinned ring + copier threads (host_staging.cuh), same kernels
     std::vector<StageArray> arrays = {{xi, nullptr, sizeof(T)}, {nullptr, yi, sizeof(T)}};
@@ -306,6 +390,7 @@ int plan1_exec_host(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t
   for (size_t off = 0; off < ni; off += cap, slot ^= 1) {
     size_t n = ni - off < cap ? ni - off : cap;
     cudaStream_t st = p->stream[slot];
+    NvtxRange nvtx_slot(slot ? "interp1:slot1 h2d+kernel+d2h" : "interp1:slot0 h2d+kernel+d2h");
     B200_CUDA(cudaMemcpyAsync(p->st_in[slot], xi + off, n * sizeof(T), cudaMemcpyHostToDevice, st));
     B200_TRY(plan1_launch<T>(p, (const T*)p->st_in[slot], n, (T*)p->st_out[slot],
                              idx ? p->st_idx[slot] : nullptr, extrap, st));
@@ -323,6 +408,7 @@ void plan1_free(b200_interp1_plan* p) {
   p->ax32.release();
   cudaFree(p->yg);
   cudaFree(p->seg);
+  cudaFree(p->binrec);
   for (int s = 0; s < 2; ++s) {
     cudaFree(p->st_in[s]); cudaFree(p->st_out[s]); cudaFree(p->st_idx[s]);
     if (p->stream[s]) cudaStreamDestroy(p->stream[s]);

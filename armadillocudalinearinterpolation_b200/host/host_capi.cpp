@@ -216,7 +216,7 @@ int b200_host_profile_stability(double beta, unsigned R, unsigned N, unsigned n_
     Stability st(Stability::ProblemType::equationFree, &map, &map);
     arma::mat J(n, n);
     map.ComputeDFDU(u, J);                                  // warm-up: allocations, NCCL channels
-    { arma::mat W(n, n, arma::fill::eye); arma::eig_gen(W); }   // ... and the eigen-solver's library / workspace
+    { arma::mat W = J + arma::mat(n, n, arma::fill::eye); arma::eig_gen(W); }   // ... and the eigen-solver's library, kernels, workspace
     auto t0 = std::chrono::steady_clock::now();
     const int unstable = st.ComputeNumUnstableEigenvalues(u);
     auto t1 = std::chrono::steady_clock::now();

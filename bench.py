@@ -254,6 +254,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE line, the JSON; whatever libraries print there on the way (NCCL's version banner
+    # of the in-process communicators, for one) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import armadillocudalinearinterpolation_b200 as B
     from armadillocudalinearinterpolation_b200 import parallel
@@ -409,6 +415,38 @@ def main():
                         "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
                     del qs, outs
                 p1.close()
+            # what bounds UNSORTED queries on a 1e6-knot grid: one L2 gather per query (the 32 MB of segment records are
+            # L2-resident); the machine's rate for that, measured live: independent 32-byte gathers from a 32 MiB table
+            g1_ms, g1_rate = L_.bench_random_gather(32 << 20, 10_000_000)
+            for kind in ("uniform", "nonuniform"):
+                rec = extra[f"interp1_f64_1e6knots_1e7queries_{kind}_unsorted"]
+                rec["l2_gather_floor"] = {"gathers_per_s": g1_rate, "us_for_1e7": g1_ms * 1e3,
+                                          "frac_of_floor": g1_ms / rec["ms_per_launch"],
+                                          "note": "1e7 independent 32-byte gathers from a 32 MiB (L2-resident) table, nothing else in the kernel"}
+            # FP32 variants of configs[0] (88 MB of algorithmic bytes)
+            xg32 = np.linspace(0.0, 1.0, ng).astype(np.float32); yg32 = np.sin(2 * np.pi * xg32).astype(np.float32)
+            xg32 = np.unique(xg32)
+            p32 = B.Interp1Plan(xg32, yg32[:xg32.size])
+            for order in ("unsorted", "sorted"):
+                g1 = torch.Generator(device="cuda").manual_seed(1236)
+                qs = [torch.rand(ni, generator=g1, device="cuda", dtype=torch.float32) for _ in range(nbuf)]
+                if order == "sorted":
+                    qs = [q.sort().values for q in qs]
+                outs = [torch.empty_like(q) for q in qs]
+                state = {"i": 0}
+
+                def step32():
+                    i = state["i"] % nbuf
+                    state["i"] += 1
+                    p32(qs[i], out=outs[i])
+                k1 = max(args.steps, 16)
+                ms1 = time_steps(torch, step32, k1, 3, dist) / k1
+                gbs = (8 * ni + 8 * xg32.size) / (ms1 * 1e-3) / 1e9
+                extra[f"interp1_f32_1e6knots_1e7queries_uniform_{order}"] = {
+                    "points_per_s": n_gpus * ni / (ms1 * 1e-3), "ms_per_launch": ms1, "lookup_mode": p32.lookup_mode,
+                    "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+                del qs, outs
+            p32.close()
             # steady state of the large-grid path: same 1e6 uniform knots, 1e8 sorted / unsorted queries in one launch
             xg = np.linspace(0.0, 1.0, ng); yg = np.sin(2 * np.pi * xg)
             p1 = B.Interp1Plan(xg, yg)
@@ -458,6 +496,22 @@ def main():
                 "algorithmic_GBps": alg_bytes / (msb * 1e-3) / 1e9, "roofline_frac": alg_bytes / (msb * 1e-3) / 1e9 / peak,
                 "bitwise_equal_to_direct_kernel": same}
             pb.close(); del zb
+            # FP32 variants of configs[1] (64 MiB grid: column-major Z is the layout the plan picks)
+            x32, y32, z32 = grid[0].astype(np.float32), grid[1].astype(np.float32), grid[2].astype(np.float32)
+            pf = B.Interp2Plan(x32, y32, z32)
+            xq32, yq32 = xq.to(torch.float32), yq.to(torch.float32)
+            zq32 = torch.empty_like(xq32)
+            nf = max(5, args.steps // 2)
+            msf = time_steps(torch, lambda: pf.scattered(xq32, yq32, out=zq32), nf, 3, dist) / nf
+            gbf = (12 * NQ + 4 * NX * NY) / (msf * 1e-3) / 1e9
+            extra["interp2_scattered_f32_4096x4096_1e8"] = {"points_per_s": n_gpus * NQ / (msf * 1e-3), "ms_per_launch": msf,
+                                                            "algorithmic_GBps": gbf, "roofline_frac": gbf / peak}
+            xi32, yi32 = xi.to(torch.float32), yi.to(torch.float32)
+            msgf = time_steps(torch, lambda: pf.grid(xi32, yi32), nf, 3, dist) / nf
+            gbgf = (4 * 1e8 + 4 * NX * NY + 8 * 1e4) / (msgf * 1e-3) / 1e9
+            extra["interp2_grid_f32_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msgf * 1e-3), "ms_per_launch": msgf,
+                                                 "algorithmic_GBps": gbgf, "roofline_frac": gbgf / peak}
+            pf.close(); del xq32, yq32, zq32
             # write-only ceiling of this GPU (a kernel that only stores): what the grid kernel is up against
             wbuf = torch.empty(NQ, dtype=torch.float64, device="cuda")
             msw = time_steps(torch, lambda: wbuf.fill_(1.5), 10, 3, dist) / 10
@@ -628,9 +682,12 @@ def main():
         v = cpu_interp2(sample, th, grid)
         line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": th, "kind": "port",
                                 "sample": f"{sample} of 1e8 scattered queries, oracle restatement of arma::interp2, OpenMP over queries"}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 

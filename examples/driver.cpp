@@ -6,6 +6,7 @@
 #include <armadillo>
 #include <chrono>
 #include <cstdlib>
+#include <iomanip>
 #include <iostream>
 #include "EventDrivenMap.hpp"
 #include "NewtonSolver.hpp"
@@ -52,7 +53,7 @@ int main(int argc, char* argv[]) {
     newton.Solve(solution, history, flag);
     const int unstable = stability.ComputeNumUnstableEigenvalues(solution);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    std::cout << "beta = " << parameters(0) << "  solution =";
+    std::cout << std::setprecision(15) << "beta = " << parameters(0) << "  solution =";
     for (arma::uword j = 0; j < solution.n_elem; ++j) std::cout << " " << solution(j);
     std::cout << "  unstable eigenvalues = " << unstable << (unstable > 0 ? "  (unstable)" : "  (stable)")
               << "  [" << ms << " ms]" << std::endl;

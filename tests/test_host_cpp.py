@@ -165,6 +165,38 @@ def test_continuation_driver_runs(host):
     assert out.stdout.count("The method converged after") == 2
 
 
+@pytest.mark.gpu
+def test_continuation_trajectory_matches_the_oracle(host, oracle):
+    """The beta-continuation of Driver.cu:86-112 (solve -> count unstable eigenvalues -> beta += 0.1 -> reuse the
+    solution), run by examples/driver.cpp through NewtonSolver / Stability / EventDrivenMapB200, against the same
+    loop on the CPU oracle: every fixed point to 1e-8 and every eigenvalue count."""
+    exe = os.path.join(LIBDIR, "driver_b200")
+    steps = 4
+    out = subprocess.run([exe, str(steps), "4", "1024", "0.1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = []
+    for l in out.stdout.splitlines():
+        if l.startswith("beta ="):
+            tok = l.split()
+            got.append((float(tok[2]), np.array([float(tok[5]), float(tok[6]), float(tok[7])]), int(tok[tok.index("eigenvalues") + 2])))
+    assert len(got) == steps
+    beta = float(np.float32(13.0589)); z = Z_DRIVER.copy()
+    for k in range(steps):
+        b32 = float(np.float32(beta))                       # SetParameters(0, (float) beta), Driver.cu:108
+        cfg = oracle.edm_cfg(R=1, N=1024, beta=b32 if k else beta)
+        f, _ = oracle.edm_compute_f(cfg, z, aux=False); it = 0
+        while np.linalg.norm(f) > 1e-4 and it < 10:
+            J, f0 = oracle.edm_compute_dfdu(cfg, z, 1e-2)
+            z = z + np.linalg.solve(J, -f0); f, _ = oracle.edm_compute_f(cfg, z, aux=False); it += 1
+        assert np.linalg.norm(f) <= 1e-4
+        J, _ = oracle.edm_compute_dfdu(cfg, z, 1e-2)
+        unstable = int(np.sum(np.abs(np.linalg.eigvals(J + np.eye(3))) > 1.0))
+        assert abs(got[k][0] - beta) < 1e-9
+        assert np.allclose(got[k][1], z, rtol=0, atol=1e-8), (k, got[k][1], z)
+        assert got[k][2] == unstable
+        beta += 0.1
+
+
 # ---- the Armadillo-facing interpolation adaptor (host/InterpB200.hpp) ----
 def test_interp_adaptor_rejects_what_it_does_not_offer(host):
     """No GPU needed: argument checks of b200::interp1 happen before any device call

@@ -151,6 +151,37 @@ def test_interp2_device_buffers(b200, oracle):
     assert same_bits(zi.cpu().numpy(), oracle.interp2_grid(x, y, z, xq[:100], yq[:64]))
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["cumsum", "clustered", "two_per_bin"])
+def test_interp1_bin_records_same_bits(b200, oracle, dt, kind, monkeypatch):
+    """Opt-in bin records for non-uniform knots (B200_INTERP1_BINREC=1: one 64-byte / 32-byte record per uniform
+    bin holding the three knots a query of that bin can need): same values and brackets as the oracle, including
+    bins with many knots (fall back to the segment records / binary search), the last knot and ragged tails."""
+    monkeypatch.setenv("B200_INTERP1_BINREC", "1")
+    rng = np.random.default_rng(31)
+    ng = 50_001
+    if kind == "cumsum":
+        xg = np.cumsum(0.5 + rng.random(ng))
+    elif kind == "clustered":
+        xg = np.concatenate([np.linspace(0, 1e-3, ng - 100), np.linspace(0.1, 1.0, 100)])
+    else:   # pairs of close knots: most bins hold two knots, the next pair is far
+        base = np.arange(ng // 2, dtype=np.float64) * 2.0
+        xg = np.sort(np.concatenate([base, base + 0.3 * rng.random(base.size) + 0.05]))
+    xg = np.unique(xg.astype(dt)); xg = ((xg - xg[0]) / (xg[-1] - xg[0])).astype(dt); xg = np.unique(xg)
+    yg = rng.standard_normal(xg.size).astype(dt)
+    xi = rng.uniform(-0.01, 1.01, 400_003).astype(dt)
+    xi[:5] = [xg[0], xg[-1], np.nan, xg[-2], np.nextafter(xg[-1], dt(2))]
+    xi[100:100 + 2000] = xg[::max(1, xg.size // 2000)][:2000]
+    plan = b200.Interp1Plan(xg, yg)
+    assert plan.lookup_mode == 1
+    yi, idx = plan(xi, extrap=-3.0, return_index=True)
+    yo, io = oracle.interp1(xg, yg, xi, extrap=-3.0, nthreads=8)
+    assert same_bits(yi, yo) and np.array_equal(idx, io)
+    yg2 = rng.standard_normal(xg.size).astype(dt)
+    plan.set_values(yg2)                                    # the records are rebuilt with the new values
+    assert same_bits(plan(xi, extrap=0.5), oracle.interp1(xg, yg2, xi, extrap=0.5, want_idx=False, nthreads=8))
+
+
 def _config1_inputs(kind):
     """BASELINE config 1 exactly as bench.py builds it (1e6 knots; SURVEY 8d seeds)."""
     ng = 1_000_000
