@@ -547,7 +547,9 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
 
   // The branchy form of the same test, neuron by neuron: fewer live registers — used by the builds capped at 64-72
   // registers (7-8 rings per SM), where the straight-line form spills inside the loop and loses (measured, round 2:
-  // 4.63 vs 3.68 ms per default evaluation; with 128 registers the straight-line form wins, 2.55 vs 2.78 ms per ring).
+  // 4.63 vs 3.62 ms per default evaluation; folding the nested tests into one predicate: 3.99 ms; handing the winner's
+  // final exponentials to the publishing thread instead of recomputing them: 3.70 ms — both spill more; with 128
+  // registers the straight-line form wins, 2.54 vs 2.78 ms per ring).
   auto scan_branchy = [&](int parity) {
 #pragma unroll
     for (int q = 0; q < NPT; ++q) {
@@ -556,31 +558,31 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       const T b = HET ? bt[q] : hb;
       const bool fo = HET ? filt[q] : h_filt;
       const T rr = s[q] * inv_vmI;
-      // stage 1 as one predicate (no nested branches): p >= 1 when r >= 1 and p >= r when r < 1 bound g from above
-      // with two FP64 operations; whole warps far from the fronts skip the block below
-      const T d1 = v[q] - k.vth;
-      const T g_ub = (rr >= one) ? d1 + (s[q] - vmI) * (HET ? ibm1[q] : h_ibm1) : (d1 - s[q]) + vmI;
-      // margin above the rounding of g_ub's own terms in the run's arithmetic (FP32: ~1e-7 relative)
-      const T m1 = sizeof(T) == 4 ? (T)1e-5 * (one + fabs(d1) + fabs(s[q])) : (T)1e-9;
-      // r < 0 or NaN: pow() is NaN, the predicate is false; r == 0 and unfiltered neurons go to the exact path
-      const bool st1 = fo ? ((rr > (T)0) ? !(g_ub < -m1) : (rr == (T)0)) : true;
-      if (st1) {
-        bool maybe = true, certain = false;
-        if (fo && rr > (T)1e-30 && rr < (T)1e30) {
+      bool maybe, certain = false;
+      if (!fo) maybe = true;
+      else if (rr > (T)0) {
+        // stage 1: p >= 1 when r >= 1 and p >= r when r < 1 bound g from above with two FP64
+        // operations; whole warps far from the fronts leave here without touching the MUFU path
+        const T d1 = v[q] - k.vth;
+        const T g_ub = (rr >= one) ? d1 + (s[q] - vmI) * (HET ? ibm1[q] : h_ibm1) : (d1 - s[q]) + vmI;
+        // margin above the rounding of g_ub's own terms in the run's arithmetic (FP32: ~1e-7 relative)
+        const T m1 = sizeof(T) == 4 ? (T)1e-5 * (one + fabs(d1) + fabs(s[q])) : (T)1e-9;
+        if (g_ub < -m1) maybe = false;
+        else if (rr > (T)1e-30 && rr < (T)1e30) {
           const float p32 = exp2f(__log2f((float)rr) * (HET ? (float)(one / b) : h_invb32));
           const T p = (T)p32;
-          const T g = d1 - vmI * ((b * p - rr) * (HET ? ibm1[q] : h_ibm1) - one);
+          const T g = (v[q] - k.vth) - vmI * ((b * p - rr) * (HET ? ibm1[q] : h_ibm1) - one);
           const T margin = (T)1e-4 * (one + p);
           maybe = !(g < -margin);
           certain = g > margin;   // the predicate is provably true: no pow() needed either
-        }
-        if (maybe) {
-          const int slot = atomicAdd(&ncand[parity], 1);
-          if (slot < (int)cap) {
-            cand_v[slot] = v[q]; cand_s[slot] = s[q];
-            cand_i[slot] = (int)j | (certain ? (int)0x80000000 : 0);
-            if (HET) cand_b[slot] = b;
-          }
+        } else maybe = true;
+      } else maybe = (rr == (T)0);  // r < 0 or NaN: pow() is NaN, the predicate is false
+      if (maybe) {
+        const int slot = atomicAdd(&ncand[parity], 1);
+        if (slot < (int)cap) {
+          cand_v[slot] = v[q]; cand_s[slot] = s[q];
+          cand_i[slot] = (int)j | (certain ? (int)0x80000000 : 0);
+          if (HET) cand_b[slot] = b;
         }
       }
     }
