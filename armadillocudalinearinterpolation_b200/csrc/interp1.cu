@@ -87,6 +87,18 @@ __device__ __forceinline__ T interp1_one(const AxisDev<T>& ax, const typename Lo
     return (q != q) ? qnan<T>() : extrap;
   }
   Seg1<T> sg;
+  if (sizeof(T) == 8 && ax.mode == 0 && !rec) {
+    // (quasi-)uniform knots, double: the common case — the arithmetic bin is the bracket, the weight operands are in
+    // the normal range — as straight-line code with the branch-free divide; anything else takes the generic walk
+    const int k = bin_of(ax, q);
+    sg = ld(k);
+    const double xa = (double)sg.xa, xb = (double)sg.xb, qq = (double)q;
+    const double a_err = __dsub_rn(qq, xa), b_err = __dsub_rn(xb, qq), sum = __dadd_rn(a_err, b_err);
+    if ((xa <= qq) && (qq < xb) && (a_err >= 0x1p-500) && (sum <= 0x1p500)) {
+      idx = k;
+      return blend((T)div_rn_fast(a_err, sum), sg.ya, sg.yb);
+    }
+  }
   if (rec) {
     const BinRec<T> r = ld_binrec(rec + bin_of(ax, q));
     const bool up1 = (r.a0 + 1 < ax.n) && (r.x[1] <= q);

@@ -412,3 +412,35 @@ def test_affine_detection_is_exact(b200, oracle):
         for flags in (0, b200.Interp2Plan.FORCE_TILES, b200.Interp2Plan.NO_CELLS | b200.Interp2Plan.NO_TILES):
             got = b200.Interp2Plan(knots, yk, z, flags=flags).scattered(xq, yq, extrap=9.0)
             assert same_bits(got, oracle.interp2_scattered(knots, yk, z, xq, yq, extrap=9.0, nthreads=8))
+
+
+def test_branch_free_divide_matches_ieee(b200):
+    """The headline interp2 kernel divides with the fast path of the IEEE divide minus its range check
+    (interp2.cu: div_rn_fast); inside its contract it must give __ddiv_rn's bits on every operand pair."""
+    import ctypes as C
+    from armadillocudalinearinterpolation_b200 import _lib
+    bad = C.c_ulonglong(123)
+    for seed in (1, 2, 3):
+        _lib.check(_lib.lib().b200_selftest_div_fast(C.c_ulonglong(400_000_000), C.c_ulonglong(seed), C.byref(bad)))
+        assert bad.value == 0
+
+
+@pytest.mark.parametrize("y_first", [False, True])
+def test_interp2_fast_kernel_special_queries(b200, oracle, y_first):
+    """The straight-line kernel (both axes affine, tile layout, double) hands every query outside its common case
+    to the generic path: out of range in either coordinate, NaN, knot hits, the last row / column, the first bin."""
+    rng = np.random.default_rng(41)
+    n = 600
+    x = np.linspace(-1.0, 2.0, n); y = np.linspace(0.0, 1.0, n + 7)
+    z = rng.standard_normal((y.size, x.size))
+    nq = 400_003
+    xq = rng.uniform(-1.2, 2.2, nq); yq = rng.uniform(-0.1, 1.1, nq)
+    xq[:8] = [x[0], x[-1], np.nan, x[5], x[-1], x[0], np.nextafter(x[-1], 0), x[-2]]
+    yq[:8] = [y[0], y[-1], 0.3, np.nan, y[0], y[-1], np.nextafter(y[-1], 0), y[-2]]
+    xq[100:100 + n] = x; yq[100:100 + n] = rng.uniform(0, 1, n)          # every x knot
+    xq[1000:1000 + y.size] = rng.uniform(-1, 2, y.size); yq[1000:1000 + y.size] = y   # every y knot
+    flags = b200.Interp2Plan.FORCE_TILES | (b200.Interp2Plan.ORDER_YX if y_first else 0)
+    plan = b200.Interp2Plan(x, y, z, flags=flags)
+    for extrap in (np.nan, 4.5):
+        ref = oracle.interp2_scattered(x, y, z, xq, yq, extrap=extrap, nthreads=8, y_first=y_first)
+        assert same_bits(plan.scattered(xq, yq, extrap=extrap), ref)
