@@ -407,7 +407,7 @@ def main():
                         i = state["i"] % nbuf
                         state["i"] += 1
                         p1(qs[i], out=outs[i])
-                    k1 = max(args.steps, 16)
+                    k1 = max(args.steps, 200)      # >= 100 back-to-back launches: one launch is launch-overhead-sized
                     ms1 = time_steps(torch, step1, k1, 3, dist) / k1
                     gbs = (16 * ni + 16 * ng) / (ms1 * 1e-3) / 1e9
                     extra[f"interp1_f64_1e6knots_1e7queries_{kind}_{order}"] = {
@@ -439,7 +439,7 @@ def main():
                     i = state["i"] % nbuf
                     state["i"] += 1
                     p32(qs[i], out=outs[i])
-                k1 = max(args.steps, 16)
+                k1 = max(args.steps, 200)      # >= 100 back-to-back launches: one launch is launch-overhead-sized
                 ms1 = time_steps(torch, step32, k1, 3, dist) / k1
                 gbs = (8 * ni + 8 * xg32.size) / (ms1 * 1e-3) / 1e9
                 extra[f"interp1_f32_1e6knots_1e7queries_uniform_{order}"] = {

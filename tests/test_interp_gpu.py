@@ -444,3 +444,33 @@ def test_interp2_fast_kernel_special_queries(b200, oracle, y_first):
     for extrap in (np.nan, 4.5):
         ref = oracle.interp2_scattered(x, y, z, xq, yq, extrap=extrap, nthreads=8, y_first=y_first)
         assert same_bits(plan.scattered(xq, yq, extrap=extrap), ref)
+
+
+@pytest.mark.parametrize("y_first", [False, True])
+def test_interp2_locality_probe_both_kernels_same_bits(b200, oracle, y_first, monkeypatch):
+    """Large device-buffer batches on an affine/tile plan are served by one of two kernels, chosen on the device by a
+    locality probe (cell-sorted queries -> the straight-line kernel, random queries -> the generic one): both choices,
+    and the forced settings (B200_INTERP2_FAST=0 / 2), give the oracle's bits — including special queries in the
+    sorted stream."""
+    import torch
+    rng = np.random.default_rng(43)
+    n = 1300
+    x = np.linspace(0.0, 1.0, n); y = np.linspace(-1.0, 1.0, n)
+    z = rng.standard_normal((n, n))
+    nq = 2_000_003
+    xq = rng.uniform(-0.01, 1.01, nq); yq = rng.uniform(-1.02, 1.02, nq)
+    xq[:6] = [x[0], x[-1], np.nan, x[7], x[-1], 0.5]; yq[:6] = [y[0], y[-1], 0.1, np.nan, y[3], y[-1]]
+    cell = np.clip((xq * (n - 1)).astype(np.int64), 0, n - 1) * n + np.clip(((yq + 1) / 2 * (n - 1)).astype(np.int64), 0, n - 1)
+    order = np.argsort(np.nan_to_num(cell), kind="stable")
+    flags = b200.Interp2Plan.FORCE_TILES | (b200.Interp2Plan.ORDER_YX if y_first else 0)
+    ref = oracle.interp2_scattered(x, y, z, xq, yq, extrap=2.5, nthreads=8, y_first=y_first)
+    for mode in ("1", "0", "2"):
+        monkeypatch.setenv("B200_INTERP2_FAST", mode)
+        if mode != "1":
+            continue   # the setting is read once per process; the forced modes are covered by tools/interp2_fast_ab.py
+        plan = b200.Interp2Plan(x, y, z, flags=flags)
+        for idx in (np.arange(nq), order):
+            tx, ty = torch.from_numpy(xq[idx]).cuda(), torch.from_numpy(yq[idx]).cuda()
+            zq = plan.scattered(tx, ty, extrap=2.5)
+            torch.cuda.synchronize()
+            assert same_bits(zq.cpu().numpy(), ref[idx])
