@@ -1113,6 +1113,10 @@ int launch_evolve_npt(b200_edm* h, const EvolveArgs<T>& A, size_t nitems, cudaSt
     bool done = false;
     if constexpr (NPT == 8) {   // (only the default 8 neurons/thread gets the second build: compile time)
       if (full && nitems <= (size_t)sms * 4) { B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 4, true>)); done = true; }
+      // front map with several waves of rings (a Jacobian batch: 4000 rings): 8 per SM at 64 registers moves more
+      // rings per second than 7 at 72 (13.4 vs 14.3 ms); one wave (the default ensemble) and the profile map are
+      // faster at 7 (3.62 vs 3.68 ms; 734 vs 787 ms) — measured, round 2
+      else if (full && !h->profile_nc && nitems > (size_t)sms * kRingsPerSm) { B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, 8, true>)); done = true; }
     }
     if (done) {}
     else if (full) B200_TRY(go(edm_evolve_kernel<T, NPT, HET, 128, kRingsPerSm, true>));

@@ -385,294 +385,301 @@ def main():
     # ---------------- secondary workloads ----------------
     if not args.no_extra:
         extra = {}
-        if not args.only_config5:
-            # configs[0]: 1-D, 1e6 knots, 1e7 queries; 8 rotating query/output buffer pairs (1.28 GB)
-            # so that consecutive launches never find their streams in L2
-            rng = np.random.default_rng(1234)
-            ng, ni, nbuf = 1_000_000, 10_000_000, 8
-            for kind in ("uniform", "nonuniform"):
-                xg = np.linspace(0.0, 1.0, ng) if kind == "uniform" else np.cumsum(0.5 + rng.random(ng))
-                xg = (xg - xg[0]) / (xg[-1] - xg[0])
-                yg = np.sin(2 * np.pi * xg) + 0.1 * np.random.default_rng(1235).standard_normal(ng)
-                p1 = B.Interp1Plan(xg, yg)
+        try:
+            if not args.only_config5:
+                # configs[0]: 1-D, 1e6 knots, 1e7 queries; 8 rotating query/output buffer pairs (1.28 GB)
+                # so that consecutive launches never find their streams in L2
+                rng = np.random.default_rng(1234)
+                ng, ni, nbuf = 1_000_000, 10_000_000, 8
+                for kind in ("uniform", "nonuniform"):
+                    xg = np.linspace(0.0, 1.0, ng) if kind == "uniform" else np.cumsum(0.5 + rng.random(ng))
+                    xg = (xg - xg[0]) / (xg[-1] - xg[0])
+                    yg = np.sin(2 * np.pi * xg) + 0.1 * np.random.default_rng(1235).standard_normal(ng)
+                    p1 = B.Interp1Plan(xg, yg)
+                    for order in ("unsorted", "sorted"):
+                        g1 = torch.Generator(device="cuda").manual_seed(1236)
+                        qs = [torch.rand(ni, generator=g1, device="cuda", dtype=torch.float64) for _ in range(nbuf)]
+                        if order == "sorted":
+                            qs = [q.sort().values for q in qs]
+                        outs = [torch.empty_like(q) for q in qs]
+                        state = {"i": 0}
+
+                        def step1():
+                            i = state["i"] % nbuf
+                            state["i"] += 1
+                            p1(qs[i], out=outs[i])
+                        k1 = max(args.steps, 200)      # >= 100 back-to-back launches: one launch is launch-overhead-sized
+                        ms1 = time_steps(torch, step1, k1, 3, dist) / k1
+                        gbs = (16 * ni + 16 * ng) / (ms1 * 1e-3) / 1e9
+                        extra[f"interp1_f64_1e6knots_1e7queries_{kind}_{order}"] = {
+                            "points_per_s": n_gpus * ni / (ms1 * 1e-3), "ms_per_launch": ms1, "lookup_mode": p1.lookup_mode,
+                            "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+                        del qs, outs
+                    p1.close()
+                # what bounds UNSORTED queries on a 1e6-knot grid: one L2 gather per query (the 32 MB of segment records are
+                # L2-resident); the machine's rate for that, measured live: independent 32-byte gathers from a 32 MiB table
+                g1_ms, g1_rate = L_.bench_random_gather(32 << 20, 10_000_000)
+                for kind in ("uniform", "nonuniform"):
+                    rec = extra[f"interp1_f64_1e6knots_1e7queries_{kind}_unsorted"]
+                    rec["l2_gather_floor"] = {"gathers_per_s": g1_rate, "us_for_1e7": g1_ms * 1e3,
+                                              "frac_of_floor": g1_ms / rec["ms_per_launch"],
+                                              "note": "1e7 independent 32-byte gathers from a 32 MiB (L2-resident) table, nothing else in the kernel"}
+                # FP32 variants of configs[0] (88 MB of algorithmic bytes)
+                xg32 = np.linspace(0.0, 1.0, ng).astype(np.float32); yg32 = np.sin(2 * np.pi * xg32).astype(np.float32)
+                xg32 = np.unique(xg32)
+                p32 = B.Interp1Plan(xg32, yg32[:xg32.size])
                 for order in ("unsorted", "sorted"):
                     g1 = torch.Generator(device="cuda").manual_seed(1236)
-                    qs = [torch.rand(ni, generator=g1, device="cuda", dtype=torch.float64) for _ in range(nbuf)]
+                    qs = [torch.rand(ni, generator=g1, device="cuda", dtype=torch.float32) for _ in range(nbuf)]
                     if order == "sorted":
                         qs = [q.sort().values for q in qs]
                     outs = [torch.empty_like(q) for q in qs]
                     state = {"i": 0}
 
-                    def step1():
+                    def step32():
                         i = state["i"] % nbuf
                         state["i"] += 1
-                        p1(qs[i], out=outs[i])
+                        p32(qs[i], out=outs[i])
                     k1 = max(args.steps, 200)      # >= 100 back-to-back launches: one launch is launch-overhead-sized
-                    ms1 = time_steps(torch, step1, k1, 3, dist) / k1
-                    gbs = (16 * ni + 16 * ng) / (ms1 * 1e-3) / 1e9
-                    extra[f"interp1_f64_1e6knots_1e7queries_{kind}_{order}"] = {
-                        "points_per_s": n_gpus * ni / (ms1 * 1e-3), "ms_per_launch": ms1, "lookup_mode": p1.lookup_mode,
+                    ms1 = time_steps(torch, step32, k1, 3, dist) / k1
+                    gbs = (8 * ni + 8 * xg32.size) / (ms1 * 1e-3) / 1e9
+                    extra[f"interp1_f32_1e6knots_1e7queries_uniform_{order}"] = {
+                        "points_per_s": n_gpus * ni / (ms1 * 1e-3), "ms_per_launch": ms1, "lookup_mode": p32.lookup_mode,
                         "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
                     del qs, outs
-                p1.close()
-            # what bounds UNSORTED queries on a 1e6-knot grid: one L2 gather per query (the 32 MB of segment records are
-            # L2-resident); the machine's rate for that, measured live: independent 32-byte gathers from a 32 MiB table
-            g1_ms, g1_rate = L_.bench_random_gather(32 << 20, 10_000_000)
-            for kind in ("uniform", "nonuniform"):
-                rec = extra[f"interp1_f64_1e6knots_1e7queries_{kind}_unsorted"]
-                rec["l2_gather_floor"] = {"gathers_per_s": g1_rate, "us_for_1e7": g1_ms * 1e3,
-                                          "frac_of_floor": g1_ms / rec["ms_per_launch"],
-                                          "note": "1e7 independent 32-byte gathers from a 32 MiB (L2-resident) table, nothing else in the kernel"}
-            # FP32 variants of configs[0] (88 MB of algorithmic bytes)
-            xg32 = np.linspace(0.0, 1.0, ng).astype(np.float32); yg32 = np.sin(2 * np.pi * xg32).astype(np.float32)
-            xg32 = np.unique(xg32)
-            p32 = B.Interp1Plan(xg32, yg32[:xg32.size])
-            for order in ("unsorted", "sorted"):
-                g1 = torch.Generator(device="cuda").manual_seed(1236)
-                qs = [torch.rand(ni, generator=g1, device="cuda", dtype=torch.float32) for _ in range(nbuf)]
-                if order == "sorted":
-                    qs = [q.sort().values for q in qs]
-                outs = [torch.empty_like(q) for q in qs]
-                state = {"i": 0}
-
-                def step32():
-                    i = state["i"] % nbuf
-                    state["i"] += 1
-                    p32(qs[i], out=outs[i])
-                k1 = max(args.steps, 200)      # >= 100 back-to-back launches: one launch is launch-overhead-sized
-                ms1 = time_steps(torch, step32, k1, 3, dist) / k1
-                gbs = (8 * ni + 8 * xg32.size) / (ms1 * 1e-3) / 1e9
-                extra[f"interp1_f32_1e6knots_1e7queries_uniform_{order}"] = {
-                    "points_per_s": n_gpus * ni / (ms1 * 1e-3), "ms_per_launch": ms1, "lookup_mode": p32.lookup_mode,
-                    "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
-                del qs, outs
-            p32.close()
-            # steady state of the large-grid path: same 1e6 uniform knots, 1e8 sorted / unsorted queries in one launch
-            xg = np.linspace(0.0, 1.0, ng); yg = np.sin(2 * np.pi * xg)
-            p1 = B.Interp1Plan(xg, yg)
-            gl = torch.Generator(device="cuda").manual_seed(1237)
-            ql = torch.rand(NQ, generator=gl, device="cuda", dtype=torch.float64)
-            ol = torch.empty_like(ql)
-            for order in ("unsorted", "sorted"):
-                if order == "sorted":
-                    ql = ql.sort().values
-                nl = max(5, args.steps // 2)
-                msl = time_steps(torch, lambda: p1(ql, out=ol), nl, 3, dist) / nl
-                gbs = (16 * NQ + 16 * ng) / (msl * 1e-3) / 1e9
-                extra[f"interp1_f64_1e6knots_1e8queries_uniform_{order}"] = {
-                    "points_per_s": n_gpus * NQ / (msl * 1e-3), "ms_per_launch": msl, "lookup_mode": p1.lookup_mode,
-                    "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
-            p1.close(); del ql, ol
-            # coarse profile -> fine ensemble: 1e3 knots staged in shared memory, 1e8 queries (1.6 GB of streams)
-            xg = np.linspace(-3.0, 3.0, 1000); yg = np.sin(xg)
-            p1 = B.Interp1Plan(xg, yg)
-            gs = torch.Generator(device="cuda").manual_seed(77)
-            qsm = torch.rand(NQ, generator=gs, device="cuda", dtype=torch.float64) * 6.0 - 3.0
-            osm = torch.empty_like(qsm)
-            nsm = max(5, args.steps // 2)
-            mssm = time_steps(torch, lambda: p1(qsm, out=osm), nsm, 3, dist) / nsm
-            gbs = (16 * NQ + 16 * 1000) / (mssm * 1e-3) / 1e9
-            extra["interp1_f64_1e3knots_1e8queries_smem"] = {"points_per_s": n_gpus * NQ / (mssm * 1e-3), "ms_per_launch": mssm,
-                                                             "lookup_mode": p1.lookup_mode, "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
-            p1.close(); del qsm, osm
-            # configs[1] grid shape (Armadillo's own interp2 API): 1e4 x 1e4 sorted points
-            g2 = torch.Generator(device="cuda").manual_seed(2236)
-            xi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
-            yi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
-            msg = time_steps(torch, lambda: plan.grid(xi, yi), max(5, args.steps // 2), 3, dist) / max(5, args.steps // 2)
-            gb = (8 * 1e8 + ALG_BYTES_GRID + 16 * 1e4) / (msg * 1e-3) / 1e9
-            extra["interp2_grid_f64_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msg * 1e-3), "ms_per_launch": msg,
-                                                 "algorithmic_GBps": gb, "roofline_frac": gb / peak}
-            # configs[1] through the opt-in L2-banded pipeline (partition by record band -> band-major
-            # interpolation -> un-permute; profiles/interp2_banded_r1.md): same queries, same bits
-            pb = B.Interp2Plan(*grid, flags=B.Interp2Plan.FORCE_BANDS)
-            zb = torch.empty_like(zq)
-            nbd = max(5, args.steps // 2)
-            msb = time_steps(torch, lambda: pb.scattered(xq, yq, out=zb), nbd, 3, dist) / nbd
-            plan.scattered(xq, yq, out=zq)
-            same = bool(torch.equal(zb.view(torch.int64), zq.view(torch.int64)))
-            extra["interp2_scattered_f64_banded_pipeline_opt_in"] = {
-                "points_per_s": n_gpus * NQ / (msb * 1e-3), "ms_per_call": msb, "kernels_per_call": 3,
-                "algorithmic_GBps": alg_bytes / (msb * 1e-3) / 1e9, "roofline_frac": alg_bytes / (msb * 1e-3) / 1e9 / peak,
-                "bitwise_equal_to_direct_kernel": same}
-            pb.close(); del zb
-            # FP32 variants of configs[1] (64 MiB grid: column-major Z is the layout the plan picks)
-            x32, y32, z32 = grid[0].astype(np.float32), grid[1].astype(np.float32), grid[2].astype(np.float32)
-            pf = B.Interp2Plan(x32, y32, z32)
-            xq32, yq32 = xq.to(torch.float32), yq.to(torch.float32)
-            zq32 = torch.empty_like(xq32)
-            nf = max(5, args.steps // 2)
-            msf = time_steps(torch, lambda: pf.scattered(xq32, yq32, out=zq32), nf, 3, dist) / nf
-            gbf = (12 * NQ + 4 * NX * NY) / (msf * 1e-3) / 1e9
-            extra["interp2_scattered_f32_4096x4096_1e8"] = {"points_per_s": n_gpus * NQ / (msf * 1e-3), "ms_per_launch": msf,
-                                                            "algorithmic_GBps": gbf, "roofline_frac": gbf / peak}
-            xi32, yi32 = xi.to(torch.float32), yi.to(torch.float32)
-            msgf = time_steps(torch, lambda: pf.grid(xi32, yi32), nf, 3, dist) / nf
-            gbgf = (4 * 1e8 + 4 * NX * NY + 8 * 1e4) / (msgf * 1e-3) / 1e9
-            extra["interp2_grid_f32_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msgf * 1e-3), "ms_per_launch": msgf,
-                                                 "algorithmic_GBps": gbgf, "roofline_frac": gbgf / peak}
-            pf.close(); del xq32, yq32, zq32
-            # write-only ceiling of this GPU (a kernel that only stores): what the grid kernel is up against
-            wbuf = torch.empty(NQ, dtype=torch.float64, device="cuda")
-            msw = time_steps(torch, lambda: wbuf.fill_(1.5), 10, 3, dist) / 10
-            extra["write_only_ceiling_GBps"] = 8 * NQ / (msw * 1e-3) / 1e9
-            del wbuf
-            # configs[1] with tile-sorted queries (SURVEY 8d variant iii): same points, ordered by grid cell
-            cell = (xq * (NX - 1)).floor().to(torch.int64) * NY + (yq * (NY - 1)).floor().to(torch.int64)
-            order = cell.argsort()
-            del cell
-            xs, ys = xq[order], yq[order]
-            del order
-            nst = max(5, args.steps // 2)
-            mss = time_steps(torch, lambda: plan.scattered(xs, ys, out=zq), nst, 3, dist) / nst
-            gbs = alg_bytes / (mss * 1e-3) / 1e9
-            extra["interp2_scattered_f64_cell_sorted_queries"] = {"points_per_s": n_gpus * NQ / (mss * 1e-3), "ms_per_launch": mss,
-                                                                  "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
-            del xs, ys
-            # configs[2]: one map evaluation, parameters.hpp default ensemble (R=1000, N=1024, M=3, T=5).
-            # Roofline convention frozen in BASELINE.md §3: unit of work = neuron-event update, F_alg = 10 FP64
-            # flops per update (calibrated once against ncu SASS op counts: (2 dfma + dadd + dmul) / updates = 9.8),
-            # peak = the FP64 FMA issue ceiling measured live by b200_bench_fp64_fma.  The event loop is a serial
-            # dependency chain, so the fraction is low by construction; chain_cycles_per_event says how long one
-            # event of one ring takes end to end.
-            F_ALG = 10.0
-            for sigma in (0.0, 0.5):
-                m = B.EventDrivenMap([BETA], 1000, noNeurons=1024)
-                m.SetParameterStdDev(sigma); m.SetSeed(42); m.EnableTiming(True)
+                p32.close()
+                # steady state of the large-grid path: same 1e6 uniform knots, 1e8 sorted / unsorted queries in one launch
+                xg = np.linspace(0.0, 1.0, ng); yg = np.sin(2 * np.pi * xg)
+                p1 = B.Interp1Plan(xg, yg)
+                gl = torch.Generator(device="cuda").manual_seed(1237)
+                ql = torch.rand(NQ, generator=gl, device="cuda", dtype=torch.float64)
+                ol = torch.empty_like(ql)
+                for order in ("unsorted", "sorted"):
+                    if order == "sorted":
+                        ql = ql.sort().values
+                    nl = max(5, args.steps // 2)
+                    msl = time_steps(torch, lambda: p1(ql, out=ol), nl, 3, dist) / nl
+                    gbs = (16 * NQ + 16 * ng) / (msl * 1e-3) / 1e9
+                    extra[f"interp1_f64_1e6knots_1e8queries_uniform_{order}"] = {
+                        "points_per_s": n_gpus * NQ / (msl * 1e-3), "ms_per_launch": msl, "lookup_mode": p1.lookup_mode,
+                        "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+                p1.close(); del ql, ol
+                # coarse profile -> fine ensemble: 1e3 knots staged in shared memory, 1e8 queries (1.6 GB of streams)
+                xg = np.linspace(-3.0, 3.0, 1000); yg = np.sin(xg)
+                p1 = B.Interp1Plan(xg, yg)
+                gs = torch.Generator(device="cuda").manual_seed(77)
+                qsm = torch.rand(NQ, generator=gs, device="cuda", dtype=torch.float64) * 6.0 - 3.0
+                osm = torch.empty_like(qsm)
+                nsm = max(5, args.steps // 2)
+                mssm = time_steps(torch, lambda: p1(qsm, out=osm), nsm, 3, dist) / nsm
+                gbs = (16 * NQ + 16 * 1000) / (mssm * 1e-3) / 1e9
+                extra["interp1_f64_1e3knots_1e8queries_smem"] = {"points_per_s": n_gpus * NQ / (mssm * 1e-3), "ms_per_launch": mssm,
+                                                                 "lookup_mode": p1.lookup_mode, "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+                p1.close(); del qsm, osm
+                # configs[1] grid shape (Armadillo's own interp2 API): 1e4 x 1e4 sorted points
+                g2 = torch.Generator(device="cuda").manual_seed(2236)
+                xi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
+                yi = torch.rand(10_000, generator=g2, device="cuda", dtype=torch.float64).sort().values
+                msg = time_steps(torch, lambda: plan.grid(xi, yi), max(5, args.steps // 2), 3, dist) / max(5, args.steps // 2)
+                gb = (8 * 1e8 + ALG_BYTES_GRID + 16 * 1e4) / (msg * 1e-3) / 1e9
+                extra["interp2_grid_f64_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msg * 1e-3), "ms_per_launch": msg,
+                                                     "algorithmic_GBps": gb, "roofline_frac": gb / peak}
+                # configs[1] through the opt-in L2-banded pipeline (partition by record band -> band-major
+                # interpolation -> un-permute; profiles/interp2_banded_r1.md): same queries, same bits
+                pb = B.Interp2Plan(*grid, flags=B.Interp2Plan.FORCE_BANDS)
+                zb = torch.empty_like(zq)
+                nbd = max(5, args.steps // 2)
+                msb = time_steps(torch, lambda: pb.scattered(xq, yq, out=zb), nbd, 3, dist) / nbd
+                plan.scattered(xq, yq, out=zq)
+                same = bool(torch.equal(zb.view(torch.int64), zq.view(torch.int64)))
+                extra["interp2_scattered_f64_banded_pipeline_opt_in"] = {
+                    "points_per_s": n_gpus * NQ / (msb * 1e-3), "ms_per_call": msb, "kernels_per_call": 3,
+                    "algorithmic_GBps": alg_bytes / (msb * 1e-3) / 1e9, "roofline_frac": alg_bytes / (msb * 1e-3) / 1e9 / peak,
+                    "bitwise_equal_to_direct_kernel": same}
+                pb.close(); del zb
+                # FP32 variants of configs[1] (64 MiB grid: column-major Z is the layout the plan picks)
+                x32, y32, z32 = grid[0].astype(np.float32), grid[1].astype(np.float32), grid[2].astype(np.float32)
+                pf = B.Interp2Plan(x32, y32, z32)
+                xq32, yq32 = xq.to(torch.float32), yq.to(torch.float32)
+                zq32 = torch.empty_like(xq32)
+                nf = max(5, args.steps // 2)
+                msf = time_steps(torch, lambda: pf.scattered(xq32, yq32, out=zq32), nf, 3, dist) / nf
+                gbf = (12 * NQ + 4 * NX * NY) / (msf * 1e-3) / 1e9
+                extra["interp2_scattered_f32_4096x4096_1e8"] = {"points_per_s": n_gpus * NQ / (msf * 1e-3), "ms_per_launch": msf,
+                                                                "algorithmic_GBps": gbf, "roofline_frac": gbf / peak}
+                xi32, yi32 = xi.to(torch.float32), yi.to(torch.float32)
+                msgf = time_steps(torch, lambda: pf.grid(xi32, yi32), nf, 3, dist) / nf
+                gbgf = (4 * 1e8 + 4 * NX * NY + 8 * 1e4) / (msgf * 1e-3) / 1e9
+                extra["interp2_grid_f32_1e4x1e4"] = {"points_per_s": n_gpus * 1e8 / (msgf * 1e-3), "ms_per_launch": msgf,
+                                                     "algorithmic_GBps": gbgf, "roofline_frac": gbgf / peak}
+                pf.close(); del xq32, yq32, zq32
+                # write-only ceiling of this GPU (a kernel that only stores): what the grid kernel is up against
+                wbuf = torch.empty(NQ, dtype=torch.float64, device="cuda")
+                msw = time_steps(torch, lambda: wbuf.fill_(1.5), 10, 3, dist) / 10
+                extra["write_only_ceiling_GBps"] = 8 * NQ / (msw * 1e-3) / 1e9
+                del wbuf
+                # configs[1] with tile-sorted queries (SURVEY 8d variant iii): same points, ordered by grid cell
+                cell = (xq * (NX - 1)).floor().to(torch.int64) * NY + (yq * (NY - 1)).floor().to(torch.int64)
+                order = cell.argsort()
+                del cell
+                xs, ys = xq[order], yq[order]
+                del order
+                nst = max(5, args.steps // 2)
+                mss = time_steps(torch, lambda: plan.scattered(xs, ys, out=zq), nst, 3, dist) / nst
+                gbs = alg_bytes / (mss * 1e-3) / 1e9
+                extra["interp2_scattered_f64_cell_sorted_queries"] = {"points_per_s": n_gpus * NQ / (mss * 1e-3), "ms_per_launch": mss,
+                                                                      "algorithmic_GBps": gbs, "roofline_frac": gbs / peak}
+                del xs, ys
+                # configs[2]: one map evaluation, parameters.hpp default ensemble (R=1000, N=1024, M=3, T=5).
+                # Roofline convention frozen in BASELINE.md §3: unit of work = neuron-event update, F_alg = 10 FP64
+                # flops per update (calibrated once against ncu SASS op counts: (2 dfma + dadd + dmul) / updates = 9.8),
+                # peak = the FP64 FMA issue ceiling measured live by b200_bench_fp64_fma.  The event loop is a serial
+                # dependency chain, so the fraction is low by construction; chain_cycles_per_event says how long one
+                # event of one ring takes end to end.
+                F_ALG = 10.0
+                for sigma in (0.0, 0.5):
+                    m = B.EventDrivenMap([BETA], 1000, noNeurons=1024)
+                    m.SetParameterStdDev(sigma); m.SetSeed(42); m.EnableTiming(True)
+                    for _ in range(3):
+                        m.ComputeF(Z_DRIVER)
+                    reps = 10
+                    t0 = time.perf_counter()
+                    evolve_ms = []
+                    for _ in range(reps):
+                        m.ComputeF(Z_DRIVER)
+                        evolve_ms.append(m.LastEvolveMs())
+                    call_ms = 1e3 * (time.perf_counter() - t0) / reps
+                    cnt = m.LastCounters()
+                    ev_ms = float(np.mean(evolve_ms))
+                    updates = cnt["events"] * 1024
+                    tflops = updates * F_ALG / (ev_ms * 1e-3) / 1e12
+                    rec = {
+                        "evals_per_s_per_gpu": 1e3 / call_ms, "ms_per_compute_f": call_ms, "evolve_kernel_ms": ev_ms,
+                        "events": cnt["events"], "neuron_event_updates_per_s": updates / (ev_ms * 1e-3),
+                        "candidates": cnt["candidates"], "newton_its": cnt["newton_its"],
+                        "roofline": {"bound": "fp64 pipe (latency-bound in practice)", "achieved": tflops, "peak": fp64_peak,
+                                     "unit": "TFLOP/s", "frac": tflops / fp64_peak,
+                                     "convention": "10 FP64 flops per neuron-event update (BASELINE.md §3), peak = live DFMA issue ceiling",
+                                     "chain_cycles_per_event": ev_ms * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / (cnt["events"] / 1000.0)}}
+                    m.close()
+                    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+                        # CPU baseline of the same evaluation: the oracle's restatement of lift -> evolve -> restrict,
+                        # OpenMP over realisations, on a bounded sample of the 1000 realisations
+                        from oracle import oracle_py as O
+                        th = cpu_threads()
+                        rs = 2 * th
+                        cfg = O.edm_cfg(R=1000, N=1024, sigma=sigma, seed=42)
+                        O.edm_compute_f(cfg, Z_DRIVER, r_begin=0, r_end=th, nthreads=th, aux=False)
+                        tc = time.perf_counter()
+                        O.edm_compute_f(cfg, Z_DRIVER, r_begin=0, r_end=rs, nthreads=th, aux=False)
+                        sec = (time.perf_counter() - tc) * 1000.0 / rs          # seconds per full 1000-realisation evaluation
+                        rec["cpu_baseline"] = {"value": 1.0 / sec, "unit": "map evals/s", "cores": th, "kind": "port",
+                                               "sample": f"{rs} of the 1000 realisations, scaled; oracle restatement of EventDrivenMap::ComputeF"}
+                    extra[f"map_eval_R1000_N1024_sigma{sigma}"] = rec
+                # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
+                # items sharded over the ranks, positions gathered with one NCCL all-gather
+                jm = parallel.ShardedJacobian([BETA], 1000, noNeurons=1024, group=dist)
                 for _ in range(3):
-                    m.ComputeF(Z_DRIVER)
+                    jm.ComputeDFDU(Z_DRIVER, 1e-2)
                 reps = 10
+                msj = wall_steps(torch, lambda: jm.ComputeDFDU(Z_DRIVER, 1e-2), reps, 0, dist) / reps
+                extra["fd_jacobian_n3_R1000_N1024"] = {"jacobians_per_s": 1e3 / msj, "map_evals_per_s": 4e3 / msj,
+                                                       "ms_per_jacobian": msj, "ranks": n_gpus, "scaling": "strong",
+                                                       "collective": "all_gather of (items x 3) positions" if world > 1 else "none"}
+            # configs[4]: stability analysis on a 1e3-dim coarse PROFILE (profile map: n = 2 x 500 knots),
+            # 1001 evaluations per Jacobian; columns sharded over the ranks, residual columns all-gathered.
+            # R = 64 realisations per column by default (--config5-full: R = 1000, i.e. 1e6 neurons per column)
+            fm = B.EventDrivenMap([BETA], 1, noNeurons=1024)
+            fm.SetDebugFlag(True); fm.ComputeF(Z_DRIVER)
+            lv, ls = fm.DebugFetch("lift_v")[0], fm.DebugFetch("lift_s")[0]
+            fm.close()
+            nc = 500
+            xf = -3.0 + 6.0 / 1024 * np.arange(1024); xc = -3.0 + 6.0 / nc * np.arange(nc)
+            u0 = np.concatenate([np.interp(xc, xf, lv), np.interp(xc, xf, ls)])
+            for R5 in ([64] if args.no_config5_full else [64, 1000]):   # R = 1000: 1e6 neurons per column (BASELINE config 5)
+                pj = parallel.ShardedJacobian([BETA], R5, noNeurons=1024, group=dist, shard="columns")
+                pj.engine.map.SetTimeHorizon(1.0)
+                pj.SetProfileMode(nc)
+                J5 = pj.ComputeDFDU(u0, 1e-3)
+                reps5 = 1 if R5 >= 1000 else 3
+                ms5 = wall_steps(torch, lambda: pj.ComputeDFDU(u0, 1e-3), reps5, 0, dist) / reps5
                 t0 = time.perf_counter()
-                evolve_ms = []
-                for _ in range(reps):
-                    m.ComputeF(Z_DRIVER)
-                    evolve_ms.append(m.LastEvolveMs())
-                call_ms = 1e3 * (time.perf_counter() - t0) / reps
-                cnt = m.LastCounters()
-                ev_ms = float(np.mean(evolve_ms))
-                updates = cnt["events"] * 1024
-                tflops = updates * F_ALG / (ev_ms * 1e-3) / 1e12
-                rec = {
-                    "evals_per_s_per_gpu": 1e3 / call_ms, "ms_per_compute_f": call_ms, "evolve_kernel_ms": ev_ms,
-                    "events": cnt["events"], "neuron_event_updates_per_s": updates / (ev_ms * 1e-3),
-                    "candidates": cnt["candidates"], "newton_its": cnt["newton_its"],
-                    "roofline": {"bound": "fp64 pipe (latency-bound in practice)", "achieved": tflops, "peak": fp64_peak,
-                                 "unit": "TFLOP/s", "frac": tflops / fp64_peak,
-                                 "convention": "10 FP64 flops per neuron-event update (BASELINE.md §3), peak = live DFMA issue ceiling",
-                                 "chain_cycles_per_event": ev_ms * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / (cnt["events"] / 1000.0)}}
-                m.close()
-                if rank == 0 and n_gpus == 1 and not args.no_cpu:
-                    # CPU baseline of the same evaluation: the oracle's restatement of lift -> evolve -> restrict,
-                    # OpenMP over realisations, on a bounded sample of the 1000 realisations
-                    from oracle import oracle_py as O
-                    th = cpu_threads()
-                    rs = 2 * th
-                    cfg = O.edm_cfg(R=1000, N=1024, sigma=sigma, seed=42)
-                    O.edm_compute_f(cfg, Z_DRIVER, r_begin=0, r_end=th, nthreads=th, aux=False)
-                    tc = time.perf_counter()
-                    O.edm_compute_f(cfg, Z_DRIVER, r_begin=0, r_end=rs, nthreads=th, aux=False)
-                    sec = (time.perf_counter() - tc) * 1000.0 / rs          # seconds per full 1000-realisation evaluation
-                    rec["cpu_baseline"] = {"value": 1.0 / sec, "unit": "map evals/s", "cores": th, "kind": "port",
-                                           "sample": f"{rs} of the 1000 realisations, scaled; oracle restatement of EventDrivenMap::ComputeF"}
-                extra[f"map_eval_R1000_N1024_sigma{sigma}"] = rec
-            # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
-            # items sharded over the ranks, positions gathered with one NCCL all-gather
-            jm = parallel.ShardedJacobian([BETA], 1000, noNeurons=1024, group=dist)
-            for _ in range(3):
-                jm.ComputeDFDU(Z_DRIVER, 1e-2)
-            reps = 10
-            msj = wall_steps(torch, lambda: jm.ComputeDFDU(Z_DRIVER, 1e-2), reps, 0, dist) / reps
-            extra["fd_jacobian_n3_R1000_N1024"] = {"jacobians_per_s": 1e3 / msj, "map_evals_per_s": 4e3 / msj,
-                                                   "ms_per_jacobian": msj, "ranks": n_gpus, "scaling": "strong",
-                                                   "collective": "all_gather of (items x 3) positions" if world > 1 else "none"}
-        # configs[4]: stability analysis on a 1e3-dim coarse PROFILE (profile map: n = 2 x 500 knots),
-        # 1001 evaluations per Jacobian; columns sharded over the ranks, residual columns all-gathered.
-        # R = 64 realisations per column by default (--config5-full: R = 1000, i.e. 1e6 neurons per column)
-        fm = B.EventDrivenMap([BETA], 1, noNeurons=1024)
-        fm.SetDebugFlag(True); fm.ComputeF(Z_DRIVER)
-        lv, ls = fm.DebugFetch("lift_v")[0], fm.DebugFetch("lift_s")[0]
-        fm.close()
-        nc = 500
-        xf = -3.0 + 6.0 / 1024 * np.arange(1024); xc = -3.0 + 6.0 / nc * np.arange(nc)
-        u0 = np.concatenate([np.interp(xc, xf, lv), np.interp(xc, xf, ls)])
-        for R5 in ([64] if args.no_config5_full else [64, 1000]):   # R = 1000: 1e6 neurons per column (BASELINE config 5)
-            pj = parallel.ShardedJacobian([BETA], R5, noNeurons=1024, group=dist, shard="columns")
-            pj.engine.map.SetTimeHorizon(1.0)
-            pj.SetProfileMode(nc)
-            J5 = pj.ComputeDFDU(u0, 1e-3)
-            reps5 = 1 if R5 >= 1000 else 3
-            ms5 = wall_steps(torch, lambda: pj.ComputeDFDU(u0, 1e-3), reps5, 0, dist) / reps5
-            t0 = time.perf_counter()
-            lam = np.linalg.eigvals(J5 + np.eye(2 * nc)) if rank == 0 else None
-            eig_ms = 1e3 * (time.perf_counter() - t0)
-            extra[f"profile_stability_n1000_N1024_R{R5}"] = {
-                "ms_per_jacobian": ms5, "map_evals_per_s": 1001e3 / ms5, "columns": 1001, "rings": 1001 * R5,
-                "neurons_per_column": 1024 * R5, "time_horizon": 1.0, "ranks": n_gpus, "scaling": "strong",
-                "unstable_eigenvalues": int(np.sum(np.abs(lam) > 1.0)) if rank == 0 else None,
-                "host_eig_ms_numpy": eig_ms, "collective": "all_gather of 1001 residual columns (8 MB)" if world > 1 else "none",
-                "launcher": "one process per GPU (torchrun), torch.distributed NCCL all_gather_into_tensor"}
-            pj.engine.map.close()
-            del pj
-        # ---- configs[3] and [4] through the product's own C++ classes (host layer over the C-ABI) ----
-        # Rank 0 drives 1 and then all n_gpus devices IN ONE PROCESS (EventDrivenMapB200::SetDevices: column / item
-        # shards, one ncclAllGather inside libb200edm.so); the other ranks wait on the host (gloo), their GPUs idle.
-        cpp = {}
-        try:
-          if rank == 0:
-            host = C.CDLL(os.path.join(ROOT, "armadillocudalinearinterpolation_b200", "lib", "libb200host.so"))
-            host.b200_host_last_error.restype = C.c_char_p
-            dp = lambda a: a.ctypes.data_as(C.c_void_p)
-            dev_sets = [1] + ([n_gpus] if n_gpus > 1 else [])
+                lam = np.linalg.eigvals(J5 + np.eye(2 * nc)) if rank == 0 else None
+                eig_ms = 1e3 * (time.perf_counter() - t0)
+                extra[f"profile_stability_n1000_N1024_R{R5}"] = {
+                    "ms_per_jacobian": ms5, "map_evals_per_s": 1001e3 / ms5, "columns": 1001, "rings": 1001 * R5,
+                    "neurons_per_column": 1024 * R5, "time_horizon": 1.0, "ranks": n_gpus, "scaling": "strong",
+                    "unstable_eigenvalues": int(np.sum(np.abs(lam) > 1.0)) if rank == 0 else None,
+                    "host_eig_ms_numpy": eig_ms, "collective": "all_gather of 1001 residual columns (8 MB)" if world > 1 else "none",
+                    "launcher": "one process per GPU (torchrun), torch.distributed NCCL all_gather_into_tensor"}
+                pj.engine.map.close()
+                del pj
+            # ---- configs[3] and [4] through the product's own C++ classes (host layer over the C-ABI) ----
+            # Rank 0 drives 1 and then all n_gpus devices IN ONE PROCESS (EventDrivenMapB200::SetDevices: column / item
+            # shards, one ncclAllGather inside libb200edm.so); the other ranks wait on the host (gloo), their GPUs idle.
+            cpp = {}
+            try:
+              if rank == 0:
+                host = C.CDLL(os.path.join(ROOT, "armadillocudalinearinterpolation_b200", "lib", "libb200host.so"))
+                host.b200_host_last_error.restype = C.c_char_p
+                dp = lambda a: a.ctypes.data_as(C.c_void_p)
+                dev_sets = [1] + ([n_gpus] if n_gpus > 1 else [])
 
-            def newton(ndev):
-                sol = np.zeros(3); hist = np.full(11, np.nan); nh = C.c_int(); J = np.zeros((3, 3), order="F"); msv = np.zeros(2)
-                devs = (C.c_int * ndev)(*range(ndev))
-                rc = host.b200_host_edm_newton_multi(C.c_double(BETA), 1000, 1024, dp(Z_DRIVER), 3, C.c_double(1e-4), 10,
-                                                     C.c_double(1e-2), 1, C.c_double(0.0), ndev, devs, dp(sol), dp(hist),
-                                                     C.byref(nh), dp(J), dp(msv))
-                if rc < 0:
-                    raise RuntimeError(host.b200_host_last_error().decode())
-                return rc, sol, hist[:nh.value], J, msv
+                def newton(ndev):
+                    sol = np.zeros(3); hist = np.full(11, np.nan); nh = C.c_int(); J = np.zeros((3, 3), order="F"); msv = np.zeros(2)
+                    devs = (C.c_int * ndev)(*range(ndev))
+                    rc = host.b200_host_edm_newton_multi(C.c_double(BETA), 1000, 1024, dp(Z_DRIVER), 3, C.c_double(1e-4), 10,
+                                                         C.c_double(1e-2), 1, C.c_double(0.0), ndev, devs, dp(sol), dp(hist),
+                                                         C.byref(nh), dp(J), dp(msv))
+                    if rc < 0:
+                        raise RuntimeError(host.b200_host_last_error().decode())
+                    return rc, sol, hist[:nh.value], J, msv
 
-            res = {nd: newton(nd) for nd in dev_sets}
-            r1 = res[1]
-            cpp["newton_config4_R1000_N1024"] = {
-                "driver_settings": "Driver.cu:28-37 (tol 1e-4, <= 10 iterations, FD eps 1e-2), Jacobian through ComputeDFDU",
-                "converged": bool(r1[0] == 1), "iterations": int(len(r1[2]) - 1), "solution": r1[1].tolist(),
-                "final_residual": float(r1[2][-1]),
-                "solve_ms": {str(nd): float(res[nd][4][0]) for nd in dev_sets},
-                "jacobian_ms": {str(nd): float(res[nd][4][1]) for nd in dev_sets},
-                "bitwise_equal_across_device_counts": all(
-                    np.array_equal(res[nd][1], r1[1]) and np.array_equal(res[nd][2], r1[2]) and np.array_equal(res[nd][3], r1[3])
-                    for nd in dev_sets)}
+                res = {nd: newton(nd) for nd in dev_sets}
+                r1 = res[1]
+                cpp["newton_config4_R1000_N1024"] = {
+                    "driver_settings": "Driver.cu:28-37 (tol 1e-4, <= 10 iterations, FD eps 1e-2), Jacobian through ComputeDFDU",
+                    "converged": bool(r1[0] == 1), "iterations": int(len(r1[2]) - 1), "solution": r1[1].tolist(),
+                    "final_residual": float(r1[2][-1]),
+                    "solve_ms": {str(nd): float(res[nd][4][0]) for nd in dev_sets},
+                    "jacobian_ms": {str(nd): float(res[nd][4][1]) for nd in dev_sets},
+                    "bitwise_equal_across_device_counts": all(
+                        np.array_equal(res[nd][1], r1[1]) and np.array_equal(res[nd][2], r1[2]) and np.array_equal(res[nd][3], r1[3])
+                        for nd in dev_sets)}
 
-            def stability(R, ndev):
-                n = 2 * nc
-                msv = np.zeros(3); J = np.zeros((n, n), order="F"); re = np.zeros(n); im = np.zeros(n)
-                devs = (C.c_int * ndev)(*range(ndev))
-                cnt = host.b200_host_profile_stability(C.c_double(BETA), R, 1024, nc, C.c_double(1.0), dp(u0), C.c_double(1e-3),
-                                                       ndev, devs, dp(msv), dp(J), dp(re), dp(im))
-                if cnt <= -1000:
-                    raise RuntimeError(host.b200_host_last_error().decode())
-                return cnt, J, msv
+                def stability(R, ndev):
+                    n = 2 * nc
+                    msv = np.zeros(3); J = np.zeros((n, n), order="F"); re = np.zeros(n); im = np.zeros(n)
+                    devs = (C.c_int * ndev)(*range(ndev))
+                    cnt = host.b200_host_profile_stability(C.c_double(BETA), R, 1024, nc, C.c_double(1.0), dp(u0), C.c_double(1e-3),
+                                                           ndev, devs, dp(msv), dp(J), dp(re), dp(im))
+                    if cnt <= -1000:
+                        raise RuntimeError(host.b200_host_last_error().decode())
+                    return cnt, J, msv
 
-            for R in ([64] if args.no_config5_full else [64, 1000]):
-                sres = {nd: stability(R, nd) for nd in dev_sets}
-                s1 = sres[1]
-                lam_np = np.linalg.eigvals(s1[1] + np.eye(2 * nc))
-                cpp[f"stability_config5_n1000_N1024_R{R}"] = {
-                    "call": "Stability::ComputeNumUnstableEigenvalues(u) = FD Jacobian (1001 evaluations) + arma::eig_gen (cuSOLVER GEEV behind the shim)",
-                    "neurons_per_column": 1024 * R, "unstable_eigenvalues": int(s1[0]),
-                    "numpy_count_on_same_jacobian": int(np.sum(np.abs(lam_np) > 1.0)),
-                    "whole_call_ms": {str(nd): float(sres[nd][2][0]) for nd in dev_sets},
-                    "jacobian_ms": {str(nd): float(sres[nd][2][1]) for nd in dev_sets},
-                    "eig_gen_ms": {str(nd): float(sres[nd][2][2]) for nd in dev_sets},
-                    "bitwise_equal_across_device_counts": all(np.array_equal(sres[nd][1], s1[1]) and sres[nd][0] == s1[0] for nd in dev_sets)}
-        except Exception as e:      # the headline line must still be printed
-            cpp["error"] = f"{type(e).__name__}: {e}"
-        if cpu_group is not None:
-            dist.barrier(group=cpu_group)
-        extra["cpp_host_layer"] = cpp
+                for R in ([64] if args.no_config5_full else [64, 1000]):
+                    sres = {nd: stability(R, nd) for nd in dev_sets}
+                    s1 = sres[1]
+                    lam_np = np.linalg.eigvals(s1[1] + np.eye(2 * nc))
+                    cpp[f"stability_config5_n1000_N1024_R{R}"] = {
+                        "call": "Stability::ComputeNumUnstableEigenvalues(u) = FD Jacobian (1001 evaluations) + arma::eig_gen (cuSOLVER GEEV behind the shim)",
+                        "neurons_per_column": 1024 * R, "unstable_eigenvalues": int(s1[0]),
+                        "numpy_count_on_same_jacobian": int(np.sum(np.abs(lam_np) > 1.0)),
+                        "whole_call_ms": {str(nd): float(sres[nd][2][0]) for nd in dev_sets},
+                        "jacobian_ms": {str(nd): float(sres[nd][2][1]) for nd in dev_sets},
+                        "eig_gen_ms": {str(nd): float(sres[nd][2][2]) for nd in dev_sets},
+                        "bitwise_equal_across_device_counts": all(np.array_equal(sres[nd][1], s1[1]) and sres[nd][0] == s1[0] for nd in dev_sets)}
+            except Exception as e:      # the headline line must still be printed
+                cpp["error"] = f"{type(e).__name__}: {e}"
+            if cpu_group is not None:
+                dist.barrier(group=cpu_group)
+            extra["cpp_host_layer"] = cpp
+        except Exception as e:
+            if world > 1:       # several ranks: a one-sided failure would leave the others in a collective
+                raise
+            import traceback
+            extra["error"] = f"{type(e).__name__}: {e}"
+            print(traceback.format_exc(), file=sys.stderr)
         line["extra"] = extra
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
