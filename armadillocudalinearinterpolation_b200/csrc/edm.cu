@@ -320,13 +320,18 @@ __device__ __forceinline__ T newton_event_time(const Consts<T>& k, T v, T s, T b
   T f = v - k.vth;         // fun(0)  : exp(0) = 1 makes every other term exactly 0
   T df = (k.I - v) + s;    // dfun(0)
   unsigned counter = 0;
+  // the Newton step f/df is formed BEFORE the stopping test of its iteration is resolved, so that the compare and
+  // the loop branch hide behind the divide's dependency chain (a warp issues in order); the step of the converged
+  // iterate is computed and dropped.  Same iterates, same stopping rule.
+  T step = fast_div(f, df);
   while (((double)fabs(f) > k.tol) && (counter < k.counter_max)) {
-    t -= fast_div(f, df);
+    t -= step;
     const T e1 = fast_exp(-t, etab);
     const T e2 = fast_exp((one - beta) * t, etab);
     const T se1 = s * e1;
     f = v * e1 + k.I * (one - e1) + se1 * i1mb * (e2 - one) - k.vth;
     df = k.I * e1 - v * e1 + se1 * e2 + (se1 * (e2 - one)) * ibm1;
+    step = fast_div(f, df);
     counter++;
   }
   its += counter;
@@ -502,19 +507,28 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   // branch (a bit per survivor), then — only in the few warps that sit on a front — stage 2 and the append.
   auto scan_straight = [&](int parity) {
     unsigned mask = 0;
+    // stage by stage over the thread's NPT neurons, not neuron by neuron: a warp issues in order, so the NPT
+    // independent dependency chains only overlap if they are interleaved in the instruction stream (the
+    // neuron-by-neuron form cost ~800 cycles per event in the single-ring profile, profiles/r2_edm_single_ring.md)
+    T rr[NPT], d1[NPT], ga[NPT], gb[NPT];
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) { rr[q] = s[q] * inv_vmI; d1[q] = v[q] - k.vth; }
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) {
+      // stage 1: p >= 1 when r >= 1 and p >= r when r < 1 bound g from above with two FP64 operations
+      ga[q] = d1[q] + (s[q] - vmI) * (HET ? ibm1[q] : h_ibm1);     // r >= 1
+      gb[q] = (d1[q] - s[q]) + vmI;                               // r <  1
+    }
 #pragma unroll
     for (int q = 0; q < NPT; ++q) {
       const unsigned j = tid + q * nthr;
       if (!FULL && j >= N) continue;
       const bool fo = HET ? filt[q] : h_filt;
-      const T rr = s[q] * inv_vmI;
-      // stage 1: p >= 1 when r >= 1 and p >= r when r < 1 bound g from above with two FP64 operations
-      const T d1 = v[q] - k.vth;
-      const T g_ub = (rr >= one) ? d1 + (s[q] - vmI) * (HET ? ibm1[q] : h_ibm1) : (d1 - s[q]) + vmI;
+      const T g_ub = (rr[q] >= one) ? ga[q] : gb[q];
       // margin above the rounding of g_ub's own terms in the run's arithmetic (FP32: ~1e-7 relative)
-      const T m1 = sizeof(T) == 4 ? (T)1e-5 * (one + fabs(d1) + fabs(s[q])) : (T)1e-9;
+      const T m1 = sizeof(T) == 4 ? (T)1e-5 * (one + fabs(d1[q]) + fabs(s[q])) : (T)1e-9;
       // r < 0 or NaN: pow() is NaN, the predicate is false; r == 0 and unfiltered neurons go to the exact path
-      const bool st1 = fo ? ((rr > (T)0) ? !(g_ub < -m1) : (rr == (T)0)) : true;
+      const bool st1 = fo ? ((rr[q] > (T)0) ? !(g_ub < -m1) : (rr[q] == (T)0)) : true;
       mask |= (st1 ? 1u : 0u) << q;
     }
     if (mask == 0) return;

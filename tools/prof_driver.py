@@ -39,3 +39,7 @@ if which in ("all", "edm"):
     m = B.EventDrivenMap([bench.BETA], 1000, noNeurons=1024)
     for _ in range(2):
         print(m.ComputeF(bench.Z_DRIVER))
+if which == "edm1":     # ONE ring alone: the serial event chain without contention (the floor of small-ensemble runs)
+    m = B.EventDrivenMap([bench.BETA], 1, noNeurons=1024)
+    for _ in range(3):
+        print(m.ComputeF(bench.Z_DRIVER))
