@@ -79,6 +79,26 @@ __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ 
   return __hiloint2double(__double2hiint(m) + (e << 20), __double2loint(m));
 }
 __device__ __forceinline__ float fast_exp(float x, const float*) { return expf(x); }
+// Two exponentials at once.  fast_exp's range test is a branch, and two calls in a row become two control-flow
+// regions that a warp executes one after the other (in-order issue): ~2 x 11 dependent FP64 operations.  One range
+// test for both arguments and the two chains written side by side let them overlap (same operations, same bits).
+__device__ __forceinline__ void fast_exp_pair(double x1, double x2, const double* __restrict__ tab, double& o1, double& o2) {
+  if (!(fabs(x1) < 690.0 && fabs(x2) < 690.0)) { o1 = fast_exp(x1, tab); o2 = fast_exp(x2, tab); return; }
+  const double t1 = fma(x1, 92.33248261689366, 6755399441055744.0), t2 = fma(x2, 92.33248261689366, 6755399441055744.0);
+  const int k1 = __double2loint(t1), k2 = __double2loint(t2);
+  const double kd1 = t1 - 6755399441055744.0, kd2 = t2 - 6755399441055744.0;
+  double r1 = fma(kd1, -0x1.62e42fee00000p-7, x1), r2 = fma(kd2, -0x1.62e42fee00000p-7, x2);
+  r1 = fma(kd1, -0x1.a39ef35793c76p-39, r1); r2 = fma(kd2, -0x1.a39ef35793c76p-39, r2);
+  const double s1 = r1 * r1, s2 = r2 * r2;
+  const double a1 = fma(r1, 1.0 / 6.0, 0.5), a2 = fma(r2, 1.0 / 6.0, 0.5);
+  const double b1 = fma(r1, 1.0 / 120.0, 1.0 / 24.0), b2 = fma(r2, 1.0 / 120.0, 1.0 / 24.0);
+  const double q1 = fma(s1, fma(s1, b1, a1), r1), q2 = fma(s2, fma(s2, b2, a2), r2);
+  const double tj1 = tab[k1 & 63], tj2 = tab[k2 & 63];
+  const double m1 = fma(tj1, q1, tj1), m2 = fma(tj2, q2, tj2);
+  o1 = __hiloint2double(__double2hiint(m1) + ((k1 >> 6) << 20), __double2loint(m1));
+  o2 = __hiloint2double(__double2hiint(m2) + ((k2 >> 6) << 20), __double2loint(m2));
+}
+__device__ __forceinline__ void fast_exp_pair(float x1, float x2, const float*, float& o1, float& o2) { o1 = expf(x1); o2 = expf(x2); }
 __device__ __forceinline__ double fast_div(double a, double b) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
@@ -326,8 +346,8 @@ __device__ __forceinline__ T newton_event_time(const Consts<T>& k, T v, T s, T b
   T step = fast_div(f, df);
   while (((double)fabs(f) > k.tol) && (counter < k.counter_max)) {
     t -= step;
-    const T e1 = fast_exp(-t, etab);
-    const T e2 = fast_exp((one - beta) * t, etab);
+    T e1, e2;
+    fast_exp_pair(-t, (one - beta) * t, etab, e1, e2);
     const T se1 = s * e1;
     f = v * e1 + k.I * (one - e1) + se1 * i1mb * (e2 - one) - k.vth;
     df = k.I * e1 - v * e1 + se1 * e2 + (se1 * (e2 - one)) * ibm1;
@@ -620,12 +640,13 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       }
     }
     m.dt = dt; m.idx = idx; m.fallback = 0;
-    const T e1 = fast_exp(-dt, etab);
+    T e1, e2 = (T)0;
+    if (!HET) fast_exp_pair(-dt, (one - hb) * dt, etab, e1, e2);
+    else e1 = fast_exp(-dt, etab);
     m.e1 = e1;
     m.cA = k.I * (one - e1);
     m.cB = m.e12 = (T)0;
     if (!HET) {
-      const T e2 = fast_exp((one - hb) * dt, etab);
       m.cB = e1 * h_i1mb * (e2 - one);
       m.e12 = e1 * e2;
     }
