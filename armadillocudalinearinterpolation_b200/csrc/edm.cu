@@ -333,7 +333,8 @@ __device__ __forceinline__ bool exact_decision(const Consts<T>& k, T v, T s, T b
 // EventDrivenMap.cu:544-573): same iterates, same stopping test as the reference.
 template <typename T>
 __device__ __forceinline__ T newton_event_time(const Consts<T>& k, T v, T s, T beta, const T* etab,
-                                               unsigned& its) {
+                                               unsigned& its, T* e1_final = nullptr, T* e2_final = nullptr,
+                                               bool* e_valid = nullptr) {
   const T one = (T)1;
   const T i1mb = fast_div(one, one - beta), ibm1 = -i1mb;
   T t = (T)0;
@@ -344,9 +345,9 @@ __device__ __forceinline__ T newton_event_time(const Consts<T>& k, T v, T s, T b
   // the loop branch hide behind the divide's dependency chain (a warp issues in order); the step of the converged
   // iterate is computed and dropped.  Same iterates, same stopping rule.
   T step = fast_div(f, df);
+  T e1 = one, e2 = one;    // exp(-t), exp((1-beta) t) at the current iterate
   while (((double)fabs(f) > k.tol) && (counter < k.counter_max)) {
     t -= step;
-    T e1, e2;
     fast_exp_pair(-t, (one - beta) * t, etab, e1, e2);
     const T se1 = s * e1;
     f = v * e1 + k.I * (one - e1) + se1 * i1mb * (e2 - one) - k.vth;
@@ -357,6 +358,9 @@ __device__ __forceinline__ T newton_event_time(const Consts<T>& k, T v, T s, T b
   its += counter;
   T out = fabs(t);
   if (out != out) out = (T)100;  // Q5: a NaN event time never wins the arg-min
+  // the exponentials of the final iterate are what the event message needs if this neuron wins (event time = t for
+  // t >= 0): handed back so that the publishing thread need not recompute them (uncapped build only)
+  if (e1_final) { *e1_final = e1; *e2_final = e2; *e_valid = (t >= (T)0) && counter > 0; }
   return out;
 }
 
@@ -551,19 +555,23 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       const bool st1 = fo ? ((rr[q] > (T)0) ? !(g_ub < -m1) : (rr[q] == (T)0)) : true;
       mask |= (st1 ? 1u : 0u) << q;
     }
-    if (mask == 0) return;
+    // stage 2 and the append for the survivors, one set bit at a time (rarely more than one per thread); the
+    // neuron's state is picked with selects, so no per-neuron branch is paid by the warps that sit on a front
+    while (mask) {
+      const int q = __ffs(mask) - 1;
+      mask &= mask - 1;
+      T vq = v[0], sq = s[0], b = HET ? bt[0] : hb, iq = HET ? ibm1[0] : h_ibm1;
+      bool fo = HET ? filt[0] : h_filt;
 #pragma unroll
-    for (int q = 0; q < NPT; ++q) {
-      if (!(mask & (1u << q))) continue;
-      const unsigned j = tid + q * nthr;
-      const T b = HET ? bt[q] : hb;
-      const bool fo = HET ? filt[q] : h_filt;
-      const T rr = s[q] * inv_vmI;
+      for (int i = 1; i < NPT; ++i)
+        if (q == i) { vq = v[i]; sq = s[i]; if (HET) { b = bt[i]; iq = ibm1[i]; fo = filt[i]; } }
+      const unsigned j = tid + (unsigned)q * nthr;
+      const T rr = sq * inv_vmI;
       bool maybe = true, certain = false;
       if (fo && rr > (T)1e-30 && rr < (T)1e30) {
         const float p32 = exp2f(__log2f((float)rr) * (HET ? (float)(one / b) : h_invb32));
         const T p = (T)p32;
-        const T g = (v[q] - k.vth) - vmI * ((b * p - rr) * (HET ? ibm1[q] : h_ibm1) - one);
+        const T g = (vq - k.vth) - vmI * ((b * p - rr) * iq - one);
         const T margin = (T)1e-4 * (one + p);
         maybe = !(g < -margin);
         certain = g > margin;   // the predicate is provably true: no pow() needed either
@@ -571,7 +579,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
       if (maybe) {
         const int slot = atomicAdd(&ncand[parity], 1);
         if (slot < (int)cap) {
-          cand_v[slot] = v[q]; cand_s[slot] = s[q];
+          cand_v[slot] = vq; cand_s[slot] = sq;
           cand_i[slot] = (int)j | (certain ? (int)0x80000000 : 0);
           if (HET) cand_b[slot] = b;
         }
@@ -628,21 +636,24 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   // The event message: (dt, idx) and the event-uniform advance coefficients.
   const bool prof = A.profile_nc != 0;
   int prof_ok = 1;
-  auto publish = [&](T dt, unsigned idx) {
+  auto publish = [&](T dt, unsigned idx, bool have_e = false, T e1w = (T)0, T e2w = (T)0) {
     EventMsg<T> m;
     m.last = 0;
     if (prof) {
       // profile map: evolve for exactly T; the event that would overshoot becomes a plain advance
-      if (!(t_now + dt <= k.T_end)) { m.last = 1; dt = k.T_end - t_now; }
+      if (!(t_now + dt <= k.T_end)) { m.last = 1; dt = k.T_end - t_now; have_e = false; }
       else {
         t_now += dt;
         if (++n_events >= 64 * (int)N) { prof_ok = 0; *stop = 1; }
       }
     }
     m.dt = dt; m.idx = idx; m.fallback = 0;
-    T e1, e2 = (T)0;
-    if (!HET) fast_exp_pair(-dt, (one - hb) * dt, etab, e1, e2);
-    else e1 = fast_exp(-dt, etab);
+    // (the winner's last Newton iterate evaluated the same exponentials of the same arguments: same bits)
+    T e1 = e1w, e2 = e2w;
+    if (!have_e) {
+      if (!HET) fast_exp_pair(-dt, (one - hb) * dt, etab, e1, e2);
+      else e1 = fast_exp(-dt, etab);
+    }
     m.e1 = e1;
     m.cA = k.I * (one - e1);
     m.cB = m.e12 = (T)0;
@@ -692,20 +703,40 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     const unsigned long long kInf = ~0ull;
     unsigned long long key = kInf;
     unsigned bidx = 0xffffffffu;
+    T my_e1 = (T)0, my_e2 = (T)0;
+    bool my_ev = false;
     for (int c = (int)tid; c < n; c += (int)nthr) {
       unsigned its = 0;
       const int ci = cand_i[c];
       const T cb = HET ? cand_b[c] : hb;
       const T cv = cand_v[c], cs = cand_s[c];
-      T tc = (T)100;
-      if (ci < 0 || exact_decision<T>(k, cv, cs, cb)) tc = newton_event_time<T>(k, cv, cs, cb, etab, its);
+      T tc = (T)100, ce1 = (T)0, ce2 = (T)0;
+      bool cev = false;
+      if (ci < 0 || exact_decision<T>(k, cv, cs, cb)) {
+        if (kStraight) tc = newton_event_time<T>(k, cv, cs, cb, etab, its, &ce1, &ce2, &cev);
+        else tc = newton_event_time<T>(k, cv, cs, cb, etab, its);
+      }
       if (A.counters) stat_newton += its;
       const unsigned long long kc = time_key(tc);
       const unsigned ic = (unsigned)(ci & 0x7fffffff);
-      if (kc < key || (kc == key && ic < bidx)) { key = kc; bidx = ic; }
+      if (kc < key || (kc == key && ic < bidx)) { key = kc; bidx = ic; if (kStraight) { my_e1 = ce1; my_e2 = ce2; my_ev = cev; } }
     }
     const bool multi = n > 32;  // block-uniform
+    const unsigned long long my_key = key;
+    const unsigned my_idx = bidx;
     if (warp == 0 || (multi && warp * 32 < (unsigned)n)) warp_argmin(key, bidx);
+    // uncapped build, single-warp case: the lane that owns the winner hands its final exponentials to thread 0
+    bool win_e = false;
+    T win_e1 = (T)0, win_e2 = (T)0;
+    if (kStraight && warp == 0 && !multi) {
+      const unsigned owner = __ballot_sync(0xffffffffu, my_key == key && my_idx == bidx && my_ev);
+      if (owner) {
+        const int src = __ffs(owner) - 1;
+        win_e1 = __shfl_sync(0xffffffffu, my_e1, src);
+        win_e2 = __shfl_sync(0xffffffffu, my_e2, src);
+        win_e = true;
+      }
+    }
     if (multi) {
       if (lane == 0) { wkey[warp] = (warp * 32 < (unsigned)n) ? key : kInf; widx[warp] = bidx; }
       __syncthreads();
@@ -729,7 +760,7 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
         T dt;
         if (sizeof(T) == 8) dt = (T)__longlong_as_double((long long)key);
         else dt = (T)__uint_as_float((unsigned)key);
-        publish(dt, bidx);
+        publish(dt, bidx, win_e, win_e1, win_e2);
       }
     }
     __syncthreads();  // B2: event message and the (late) loop condition are visible
