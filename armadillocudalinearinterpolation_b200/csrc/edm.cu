@@ -534,26 +534,33 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     // stage by stage over the thread's NPT neurons, not neuron by neuron: a warp issues in order, so the NPT
     // independent dependency chains only overlap if they are interleaved in the instruction stream (the
     // neuron-by-neuron form cost ~800 cycles per event in the single-ring profile, profiles/r2_edm_single_ring.md)
-    T rr[NPT], d1[NPT], ga[NPT], gb[NPT];
+    // (GS neurons at a time: all NPT with 128 registers, half of them in the register-capped build)
+    constexpr int GS = (MINB <= 4) ? NPT : (NPT >= 4 ? NPT / 2 : NPT);
 #pragma unroll
-    for (int q = 0; q < NPT; ++q) { rr[q] = s[q] * inv_vmI; d1[q] = v[q] - k.vth; }
+    for (int g0 = 0; g0 < NPT; g0 += GS) {
+      T rr[GS], d1[GS], ga[GS], gb[GS];
 #pragma unroll
-    for (int q = 0; q < NPT; ++q) {
-      // stage 1: p >= 1 when r >= 1 and p >= r when r < 1 bound g from above with two FP64 operations
-      ga[q] = d1[q] + (s[q] - vmI) * (HET ? ibm1[q] : h_ibm1);     // r >= 1
-      gb[q] = (d1[q] - s[q]) + vmI;                               // r <  1
-    }
+      for (int i = 0; i < GS; ++i) { const int q = g0 + i; rr[i] = s[q] * inv_vmI; d1[i] = v[q] - k.vth; }
 #pragma unroll
-    for (int q = 0; q < NPT; ++q) {
-      const unsigned j = tid + q * nthr;
-      if (!FULL && j >= N) continue;
-      const bool fo = HET ? filt[q] : h_filt;
-      const T g_ub = (rr[q] >= one) ? ga[q] : gb[q];
-      // margin above the rounding of g_ub's own terms in the run's arithmetic (FP32: ~1e-7 relative)
-      const T m1 = sizeof(T) == 4 ? (T)1e-5 * (one + fabs(d1[q]) + fabs(s[q])) : (T)1e-9;
-      // r < 0 or NaN: pow() is NaN, the predicate is false; r == 0 and unfiltered neurons go to the exact path
-      const bool st1 = fo ? ((rr[q] > (T)0) ? !(g_ub < -m1) : (rr[q] == (T)0)) : true;
-      mask |= (st1 ? 1u : 0u) << q;
+      for (int i = 0; i < GS; ++i) {
+        const int q = g0 + i;
+        // stage 1: p >= 1 when r >= 1 and p >= r when r < 1 bound g from above with two FP64 operations
+        ga[i] = d1[i] + (s[q] - vmI) * (HET ? ibm1[q] : h_ibm1);     // r >= 1
+        gb[i] = (d1[i] - s[q]) + vmI;                               // r <  1
+      }
+#pragma unroll
+      for (int i = 0; i < GS; ++i) {
+        const int q = g0 + i;
+        const unsigned j = tid + q * nthr;
+        if (!FULL && j >= N) continue;
+        const bool fo = HET ? filt[q] : h_filt;
+        const T g_ub = (rr[i] >= one) ? ga[i] : gb[i];
+        // margin above the rounding of g_ub's own terms in the run's arithmetic (FP32: ~1e-7 relative)
+        const T m1 = sizeof(T) == 4 ? (T)1e-5 * (one + fabs(d1[i]) + fabs(s[q])) : (T)1e-9;
+        // r < 0 or NaN: pow() is NaN, the predicate is false; r == 0 and unfiltered neurons go to the exact path
+        const bool st1 = fo ? ((rr[i] > (T)0) ? !(g_ub < -m1) : (rr[i] == (T)0)) : true;
+        mask |= (st1 ? 1u : 0u) << q;
+      }
     }
     // stage 2 and the append for the survivors, one set bit at a time (rarely more than one per thread); the
     // neuron's state is picked with selects, so no per-neuron branch is paid by the warps that sit on a front
@@ -631,7 +638,11 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
   };
 
   constexpr bool kStraight = (MINB <= 4);
+#ifdef B200_EDM_CAPPED_STRAIGHT   // experiment hook: the stage-wise scan (4 neurons at a time) on the capped build — 3.61 vs 3.31 ms, not taken
+  auto scan = [&](int parity) { scan_straight(parity); };
+#else
   auto scan = [&](int parity) { if (kStraight) scan_straight(parity); else scan_branchy(parity); };
+#endif
 
   // The event message: (dt, idx) and the event-uniform advance coefficients.
   const bool prof = A.profile_nc != 0;
