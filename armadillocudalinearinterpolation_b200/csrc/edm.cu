@@ -99,6 +99,40 @@ __device__ __forceinline__ void fast_exp_pair(double x1, double x2, const double
   o2 = __hiloint2double(__double2hiint(m2) + ((k2 >> 6) << 20), __double2loint(m2));
 }
 __device__ __forceinline__ void fast_exp_pair(float x1, float x2, const float*, float& o1, float& o2) { o1 = expf(x1); o2 = expf(x2); }
+// G exponentials at once, written stage by stage so that the G chains overlap (heterogeneous ensembles need one
+// exponential per neuron and event: eight calls in a row were eight serial regions)
+template <int G>
+__device__ __forceinline__ void fast_exp_vec(const double (&x)[G], const double* __restrict__ tab, double (&o)[G]) {
+  bool in = true;
+#pragma unroll
+  for (int i = 0; i < G; ++i) in = in && (fabs(x[i]) < 690.0);
+  if (!in) {
+#pragma unroll
+    for (int i = 0; i < G; ++i) o[i] = fast_exp(x[i], tab);
+    return;
+  }
+  double t[G], r[G], q[G], tj[G];
+  int k[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) { t[i] = fma(x[i], 92.33248261689366, 6755399441055744.0); k[i] = __double2loint(t[i]); }
+#pragma unroll
+  for (int i = 0; i < G; ++i) { const double kd = t[i] - 6755399441055744.0; r[i] = fma(kd, -0x1.a39ef35793c76p-39, fma(kd, -0x1.62e42fee00000p-7, x[i])); tj[i] = tab[k[i] & 63]; }
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const double r2 = r[i] * r[i];
+    q[i] = fma(r2, fma(r2, fma(r[i], 1.0 / 120.0, 1.0 / 24.0), fma(r[i], 1.0 / 6.0, 0.5)), r[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const double m = fma(tj[i], q[i], tj[i]);
+    o[i] = __hiloint2double(__double2hiint(m) + ((k[i] >> 6) << 20), __double2loint(m));
+  }
+}
+template <int G>
+__device__ __forceinline__ void fast_exp_vec(const float (&x)[G], const float*, float (&o)[G]) {
+#pragma unroll
+  for (int i = 0; i < G; ++i) o[i] = expf(x[i]);
+}
 __device__ __forceinline__ double fast_div(double a, double b) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
@@ -823,19 +857,34 @@ edm_evolve_kernel(const EvolveArgs<T> A) {
     //      (EventDrivenMap.cu:612-618), then test who can fire next ----
     parity ^= 1;
     const int rel0 = (int)tid - (int)m.idx;
+    if (HET) {
+      // one exponential per neuron (its own beta): four neurons at a time, their chains side by side
+      constexpr int GE = NPT >= 4 ? 4 : NPT;
 #pragma unroll
-    for (int q = 0; q < NPT; ++q) {
-      const unsigned j = tid + q * nthr;
-      if (!FULL && j >= N) continue;
-      const unsigned dist = (unsigned)abs(rel0 + q * (int)nthr);
-      if (HET) {
-        const T b = bt[q];
-        const T e2 = fast_exp((one - b) * m.dt, etab);
-        const T cB = m.e1 * (-ibm1[q]) * (e2 - one);
-        T vn = v[q] * m.e1 + (m.cA + s[q] * cB);
-        v[q] = (!(FULL && kStraight) && dist == 0) ? (T)0 : vn;
-        s[q] = s[q] * (m.e1 * e2) + b * bw[dist];
-      } else {
+      for (int g0 = 0; g0 < NPT; g0 += GE) {
+        T xe[GE], e2[GE];
+#pragma unroll
+        for (int i = 0; i < GE; ++i) xe[i] = (one - bt[g0 + i]) * m.dt;
+        fast_exp_vec<GE>(xe, etab, e2);
+#pragma unroll
+        for (int i = 0; i < GE; ++i) {
+          const int q = g0 + i;
+          const unsigned j = tid + q * nthr;
+          if (!FULL && j >= N) continue;
+          const unsigned dist = (unsigned)abs(rel0 + q * (int)nthr);
+          const T b = bt[q];
+          const T cB = m.e1 * (-ibm1[q]) * (e2[i] - one);
+          T vn = v[q] * m.e1 + (m.cA + s[q] * cB);
+          v[q] = (!(FULL && kStraight) && dist == 0) ? (T)0 : vn;
+          s[q] = s[q] * (m.e1 * e2[i]) + b * bw[dist];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) {
+        const unsigned j = tid + q * nthr;
+        if (!FULL && j >= N) continue;
+        const unsigned dist = (unsigned)abs(rel0 + q * (int)nthr);
         T vn = v[q] * m.e1 + (m.cA + s[q] * m.cB);
         v[q] = (!(FULL && kStraight) && dist == 0) ? (T)0 : vn;
         s[q] = s[q] * m.e12 + bw[dist];
