@@ -364,6 +364,11 @@ def main():
                                               "note": "same call with ordinary (pageable) numpy / arma::vec buffers"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_note,
+                         # what the DRAM interface actually moved: every L2 miss of a random query fills a whole
+                         # 128-byte line although 32 bytes of it are used, so the kernel saturates HBM in real bytes
+                         # (this line) while its algorithmic bytes are a quarter of that (`frac`)
+                         "dram_GBps_actual": (traffic / (ms_per_step * 1e6)) if traffic else None,
+                         "dram_frac_of_peak_actual": (traffic / (ms_per_step * 1e6) / peak) if traffic else None,
                          "peak_source": peak_src, "kernel": "interp2_scattered_smem_kernel<double, tiles>",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          # what bounds uniformly random queries on a 128 MiB grid, as numbers: one table line per
