@@ -23,6 +23,21 @@ struct NvtxRange {
   NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
+// Entry points run on the device their plan / handle lives on and hand the caller's current device back on
+// every exit path (dev < 0: only restore — for functions that switch between several devices themselves).
+struct DeviceScope {
+  int prev = -1;
+  bool restore = false;
+  explicit DeviceScope(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (dev < 0) { restore = true; return; }
+    if (dev != prev) { cudaSetDevice(dev); restore = true; }
+  }
+  ~DeviceScope() { if (restore) cudaSetDevice(prev); }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
 int fail(int status, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // B200_OK if the current device is a compute-capability 10.x GPU (there is no CPU path).

@@ -1441,18 +1441,20 @@ int ensure_u(b200_edm* g, size_t n) {
 int exchange_slots(b200_edm* h, cudaStream_t st, size_t slot_bytes, size_t acc_slot_items) {
   const size_t ndev = h->helpers.size() + 1;
   if (!h->comms.empty()) {
-    nvtxRangePushA("edm:nccl_all_gather");
+    NvtxRange nvtx("edm:nccl_all_gather");
     B200_NCCL(g_nccl.group_start());
-    for (size_t d = 0; d < ndev; ++d) {
+    ncclResult_t bad = ncclSuccess;   // a failed call must not leave the thread inside an open group
+    for (size_t d = 0; d < ndev && bad == ncclSuccess; ++d) {
       b200_edm* g = dev_handle(h, d);
       cudaStream_t gs = d == 0 ? st : g->stream;
       if (slot_bytes)
-        B200_NCCL(g_nccl.all_gather((const char*)g->d_gather + d * slot_bytes, g->d_gather, slot_bytes, ncclChar, h->comms[d], gs));
-      if (acc_slot_items)
-        B200_NCCL(g_nccl.all_gather(g->d_gather_acc + d * acc_slot_items, g->d_gather_acc, acc_slot_items, ncclInt32, h->comms[d], gs));
+        bad = g_nccl.all_gather((const char*)g->d_gather + d * slot_bytes, g->d_gather, slot_bytes, ncclChar, h->comms[d], gs);
+      if (acc_slot_items && bad == ncclSuccess)
+        bad = g_nccl.all_gather(g->d_gather_acc + d * acc_slot_items, g->d_gather_acc, acc_slot_items, ncclInt32, h->comms[d], gs);
     }
-    B200_NCCL(g_nccl.group_end());
-    nvtxRangePop();
+    const ncclResult_t end = g_nccl.group_end();
+    if (bad != ncclSuccess) return fail(B200_ERR_CUDA, "NCCL error %d (%s) in ncclAllGather", (int)bad, g_nccl.error_string(bad));
+    if (end != ncclSuccess) return fail(B200_ERR_CUDA, "NCCL error %d (%s) in ncclGroupEnd", (int)end, g_nccl.error_string(end));
     return B200_OK;
   }
   for (size_t d = 1; d < ndev; ++d) {
@@ -1483,6 +1485,7 @@ int exchange_slots(b200_edm* h, cudaStream_t st, size_t slot_bytes, size_t acc_s
 template <typename T>
 int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, bool fd, double eps, double* out_cols,
                   double* f0_out) {
+  DeviceScope callers_device(-1);   // the loop below switches devices; the caller gets its own back on every exit
   B200_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   const size_t ndev = h->helpers.size() + 1, R = h->R, nd = ndim(h), es = esize(h);
@@ -1516,7 +1519,8 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
     if (by_columns) B200_TRY(ensure_gather(g, ndev * cpd * nd * sizeof(double), 0));
     else B200_TRY(ensure_gather(g, ndev * per * nd * es, ndev * per));
     if (cols_res == 0 && by_columns) continue;                 // more devices than columns: idle, still joins the gather
-    nvtxRangePushA("edm:lift");
+    {
+    NvtxRange nvtx("edm:lift");
     if (fd) {
       B200_TRY(ensure_u(g, n));
       if (g->up_pending) { B200_CUDA(cudaEventSynchronize(g->ev_up)); g->up_pending = false; }
@@ -1533,16 +1537,17 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
       B200_TRY(upload_z(g, z_or_u + c_lo * n, n, cols_loc, gs));
     }
     B200_TRY(run_prepare<T>(g, cols_loc, gs));
-    nvtxRangePop();
-    nvtxRangePushA("edm:evolve");
-    if (by_columns) {
-      B200_TRY(run_evolve<T>(g, 0, cols_loc * R, (T*)g->d_pos, g->d_accept, gs));
-    } else {
-      B200_TRY(run_evolve<T>(g, i_lo, i_hi, (T*)((char*)g->d_gather + d * per * nd * es), g->d_gather_acc + d * per, gs));
     }
-    nvtxRangePop();
+    {
+      NvtxRange nvtx("edm:evolve");
+      if (by_columns) {
+        B200_TRY(run_evolve<T>(g, 0, cols_loc * R, (T*)g->d_pos, g->d_accept, gs));
+      } else {
+        B200_TRY(run_evolve<T>(g, i_lo, i_hi, (T*)((char*)g->d_gather + d * per * nd * es), g->d_gather_acc + d * per, gs));
+      }
+    }
     if (by_columns) {
-      nvtxRangePushA("edm:reduce");
+      NvtxRange nvtx("edm:reduce");
       double* slot = (double*)g->d_gather + d * cpd * nd;
       if (fd) {
         B200_TRY(run_reduce<T>(g, cols_loc, (const T*)g->d_pos, g->d_accept, g->d_f, gs));
@@ -1553,7 +1558,6 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
       } else {
         B200_TRY(run_reduce<T>(g, cols_loc, (const T*)g->d_pos, g->d_accept, slot, gs));
       }
-      nvtxRangePop();
     }
   }
   B200_CUDA(cudaSetDevice(h->device));
@@ -1568,7 +1572,7 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
     if (fd) d_f0 = h->d_f + (((cpd < ncols ? cpd : ncols)) * n);     // the primary's base column (local column cols_res)
   } else {
     // item mode: all positions are here in item order; the usual fixed-order reduction over every column
-    nvtxRangePushA("edm:reduce");
+    NvtxRange nvtx("edm:reduce");
     B200_TRY(run_reduce<T>(h, ncols + (fd ? 1 : 0), (const T*)h->d_gather, h->d_gather_acc, h->d_f, st));
     if (fd) {
       const size_t total = ncols * n;
@@ -1585,7 +1589,6 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
     } else {
       d_result = h->d_f;
     }
-    nvtxRangePop();
   }
   double* h_res = h->h_pin + n * (ncols + 1);
   B200_CUDA(cudaMemcpyAsync(h_res, d_result, n * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1654,6 +1657,7 @@ int b200_edm_create(const double* params, size_t nparams, uint32_t no_realisatio
 
 int b200_edm_destroy(b200_edm* h) {
   if (!h) return B200_OK;
+  DeviceScope callers_device(-1);
   for (b200_edm* g : h->helpers) b200_edm_destroy(g);
   h->helpers.clear();
   if (!h->comms.empty() && g_nccl.ok) for (ncclComm_t c : h->comms) g_nccl.comm_destroy(c);
@@ -1696,14 +1700,14 @@ int b200_edm_set_time_horizon(b200_edm* h, double T) {
 int b200_edm_set_no_realisations(b200_edm* h, uint32_t R) {
   B200_TRY(check_handle(h, "edm_set_no_realisations"));
   if (R < 1) return fail(B200_ERR_INVALID_ARG, "no_realisations must be > 0 (EventDrivenMap.cu:251)");
-  if (R != h->R) { h->R = R; h->beta_dirty = true; cudaSetDevice(h->device); free_batch(h); }
+  if (R != h->R) { DeviceScope on_handle_device(h->device); h->R = R; h->beta_dirty = true; free_batch(h); }
   return B200_OK;
 }
 int b200_edm_set_no_neurons(b200_edm* h, uint32_t N) {
   B200_TRY(check_handle(h, "edm_set_no_neurons"));
   if (N < 2) return fail(B200_ERR_INVALID_ARG, "no_neurons must be >= 2 (EventDrivenMap.cu:284)");
   if (N > 16384) return fail(B200_ERR_UNSUPPORTED, "no_neurons > 16384 (one CTA holds a whole ring)");
-  if (N != h->N) { h->N = N; h->w_dirty = h->beta_dirty = true; cudaSetDevice(h->device); free_batch(h); }
+  if (N != h->N) { DeviceScope on_handle_device(h->device); h->N = N; h->w_dirty = h->beta_dirty = true; free_batch(h); }
   return B200_OK;
 }
 int b200_edm_set_param_stddev(b200_edm* h, double sigma) {
@@ -1711,7 +1715,7 @@ int b200_edm_set_param_stddev(b200_edm* h, double sigma) {
   if (!(sigma >= 0)) return fail(B200_ERR_INVALID_ARG, "sigma must be >= 0 (EventDrivenMap.cu:319)");
   if (sigma != h->sigma) {
     h->sigma = sigma; h->beta_dirty = true;
-    if (sigma == 0.0) { cudaSetDevice(h->device); cudaFree(h->beta); h->beta = nullptr; }   // no stale ensemble behind DBG_BETA
+    if (sigma == 0.0) { DeviceScope on_handle_device(h->device); cudaFree(h->beta); h->beta = nullptr; }   // no stale ensemble behind DBG_BETA
   }
   return B200_OK;
 }
@@ -1746,6 +1750,7 @@ int b200_edm_new_seed(b200_edm* h) {
 int b200_edm_set_devices(b200_edm* h, const int* device_ids, size_t ndevices) {
   B200_TRY(check_handle(h, "edm_set_devices"));
   if (!device_ids || ndevices < 1) return fail(B200_ERR_INVALID_ARG, "edm_set_devices: empty device list");
+  DeviceScope callers_device(-1);
   if (device_ids[0] != h->device) return fail(B200_ERR_INVALID_ARG, "edm_set_devices: the first device must be the handle's own (%d)", h->device);
   int count = 0;
   B200_CUDA(cudaGetDeviceCount(&count));
@@ -1795,7 +1800,7 @@ int b200_edm_set_devices(b200_edm* h, const int* device_ids, size_t ndevices) {
 int b200_edm_set_profile_mode(b200_edm* h, uint32_t n_coarse) {
   B200_TRY(check_handle(h, "edm_set_profile_mode"));
   if (n_coarse == 1) return fail(B200_ERR_INVALID_ARG, "profile map needs at least 2 coarse knots (0 switches it off)");
-  if (n_coarse != h->profile_nc) { cudaSetDevice(h->device); free_batch(h); h->profile_nc = n_coarse; h->last_cols = 0; }
+  if (n_coarse != h->profile_nc) { DeviceScope on_handle_device(h->device); free_batch(h); h->profile_nc = n_coarse; h->last_cols = 0; }
   return B200_OK;
 }
 
@@ -1839,7 +1844,7 @@ int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
     return fail(B200_ERR_INVALID_ARG, "edm_evolve_items_dev: bad item range / NULL argument");
   const size_t nitems = item_end - item_begin;
   if (nitems && (!pos_dev || !accept_dev)) return fail(B200_ERR_INVALID_ARG, "edm_evolve_items_dev: NULL output");
-  B200_CUDA(cudaSetDevice(h->device));
+  DeviceScope on_handle_device(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   B200_TRY(order_after_previous(h, st));
   B200_TRY(ensure_batch(h, ncols, nitems ? nitems : 1));
@@ -1869,7 +1874,7 @@ int b200_edm_reduce_items_dev(b200_edm* h, const double* z_cols, size_t n, size_
   B200_TRY(check_handle(h, "edm_reduce_items_dev"));
   if (!z_cols || !pos_all_dev || !accept_all_dev || !f_cols_dev || ncols < 1)
     return fail(B200_ERR_INVALID_ARG, "edm_reduce_items_dev: NULL / empty argument");
-  B200_CUDA(cudaSetDevice(h->device));
+  DeviceScope on_handle_device(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   B200_TRY(order_after_previous(h, st));
   B200_TRY(ensure_batch(h, ncols, 1));
@@ -1932,7 +1937,7 @@ int b200_edm_debug_fetch(b200_edm* h, b200_edm_debug_what what, void* out, size_
   if (!out) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: NULL output");
   if (!h->debug) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: debug flag is off (SetDebugFlag)");
   if (h->last_cols == 0) return fail(B200_ERR_INVALID_ARG, "edm_debug_fetch: no evaluation has run yet");
-  B200_CUDA(cudaSetDevice(h->device));
+  DeviceScope on_handle_device(h->device);
   const size_t C = h->last_cols, R = h->R, N = h->N, Mf = ndim(h), es = esize(h);
   if (h->profile_nc && what != B200_EDM_DBG_LIFT_V && what != B200_EDM_DBG_LIFT_S && what != B200_EDM_DBG_ACCEPT &&
       what != B200_EDM_DBG_POSITION && what != B200_EDM_DBG_EVENT_COUNT && what != B200_EDM_DBG_BETA &&

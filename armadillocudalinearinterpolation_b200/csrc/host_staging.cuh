@@ -57,6 +57,12 @@ struct StagePool {
     for (size_t a = 0; same && a < arrays.size(); ++a) same = elems[a] == arrays[a].elem;
     if (same) return B200_OK;
     release();
+    const int rc = build(dev_id, nworkers, chunk_elems, arrays);
+    if (rc != B200_OK) release();   // never leave a half-built pool behind: the next call would take it for complete
+    return rc;
+  }
+
+  int build(int dev_id, int nworkers, size_t chunk_elems, const std::vector<StageArray>& arrays) {
     device = dev_id;
     chunk = chunk_elems;
     for (const StageArray& a : arrays) elems.push_back(a.elem);
@@ -129,9 +135,15 @@ int staged_run(StagePool& pool, int device, const std::vector<StageArray>& array
     if (status[t] != B200_OK) text[t] = b200_last_error();   // the error text is thread-local: carry it over
   };
   std::vector<std::thread> th;
-  for (int t = 1; t < nworkers; ++t) th.emplace_back(body, t);
+  bool spawn_failed = false;
+  try {
+    for (int t = 1; t < nworkers; ++t) th.emplace_back(body, t);
+  } catch (...) {   // no exception may cross the C ABI; the chunks of the missing workers are not done -> the call fails
+    spawn_failed = true;
+  }
   body(0);
   for (std::thread& x : th) x.join();
+  if (spawn_failed) return fail(B200_ERR_CUDA, "staged copy: could not start the worker threads");
   for (int t = 0; t < nworkers; ++t)
     if (status[t] != B200_OK) return fail(status[t], "%s", text[t].c_str());
   return B200_OK;

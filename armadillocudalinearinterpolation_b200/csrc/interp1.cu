@@ -453,6 +453,7 @@ int b200_interp1_plan_create(b200_dtype dtype, const void* xg, const void* yg, s
 
 int b200_interp1_plan_set_values(b200_interp1_plan* p, const void* yg) {
   if (!p || !yg) return fail(B200_ERR_INVALID_ARG, "interp1_plan_set_values: NULL argument");
+  DeviceScope on_plan_device(p->device);
   size_t esz = p->dtype == B200_F64 ? 8 : 4;
   B200_CUDA(cudaMemcpyAsync(p->yg, yg, p->ng * esz, cudaMemcpyHostToDevice, p->stream[0]));
   B200_TRY(p->dtype == B200_F64 ? plan1_build_seg<double>(p, p->stream[0]) : plan1_build_seg<float>(p, p->stream[0]));
@@ -461,7 +462,7 @@ int b200_interp1_plan_set_values(b200_interp1_plan* p, const void* yg) {
 }
 
 int b200_interp1_plan_destroy(b200_interp1_plan* p) {
-  if (p) plan1_free(p);
+  if (p) { DeviceScope on_plan_device(p->device); plan1_free(p); }
   return B200_OK;
 }
 
@@ -474,6 +475,7 @@ int b200_interp1_plan_lookup_mode(const b200_interp1_plan* p) {
 int b200_interp1_exec(b200_interp1_plan* p, const void* xi, size_t ni, void* yi, int32_t* idx_out,
                       double extrap_val) {
   if (!p || (ni && (!xi || !yi))) return fail(B200_ERR_INVALID_ARG, "interp1_exec: NULL argument");
+  DeviceScope on_plan_device(p->device);
   return p->dtype == B200_F64
              ? plan1_exec_host<double>(p, (const double*)xi, ni, (double*)yi, idx_out, extrap_val)
              : plan1_exec_host<float>(p, (const float*)xi, ni, (float*)yi, idx_out, (float)extrap_val);
@@ -482,6 +484,7 @@ int b200_interp1_exec(b200_interp1_plan* p, const void* xi, size_t ni, void* yi,
 int b200_interp1_exec_dev(b200_interp1_plan* p, const void* xi_dev, size_t ni, void* yi_dev,
                           int32_t* idx_dev, double extrap_val, void* stream) {
   if (!p || (ni && (!xi_dev || !yi_dev))) return fail(B200_ERR_INVALID_ARG, "interp1_exec_dev: NULL argument");
+  DeviceScope on_plan_device(p->device);
   cudaStream_t st = (cudaStream_t)stream;
   return p->dtype == B200_F64
              ? plan1_launch<double>(p, (const double*)xi_dev, ni, (double*)yi_dev, idx_dev, extrap_val, st)

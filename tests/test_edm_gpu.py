@@ -224,6 +224,16 @@ def test_in_process_multi_device_is_bitwise_single_device(b200):
     assert np.array_equal(Ja, Jb) and np.array_equal(fa, fb)
     uc = np.stack([u * (1 + 1e-3 * k) for k in range(40)], axis=1)
     assert np.array_equal(a.ComputeFBatch(uc), b.ComputeFBatch(uc))
+    # the library hands the caller's current device back, whichever device it was (the map lives on device 0)
+    import torch
+    torch.cuda.set_device(n_dev - 1)
+    try:
+        fb = b.ComputeF(u)
+        assert torch.cuda.current_device() == n_dev - 1
+        assert np.array_equal(fb, a.ComputeF(u))
+        assert torch.cuda.current_device() == n_dev - 1
+    finally:
+        torch.cuda.set_device(0)
 
 
 def test_drive_above_threshold_bypasses_the_candidate_filter(b200, oracle):
