@@ -87,7 +87,12 @@ extern "C" int b200_eig_gen_f64(size_t n, const double* a_colmajor, double* w_re
       g_states.pop_back();
       return fail(B200_ERR_CUDA, "eig_gen: cusolverDnCreate failed");
     }
-    B200_CUDA(cudaMalloc(&st->dInfo, sizeof(int)));
+    if (cudaMalloc(&st->dInfo, sizeof(int)) != cudaSuccess) {   // never keep a half-initialised state for the next call
+      cudaGetLastError();
+      s.destroy_params(st->pr); s.destroy(st->hd);
+      g_states.pop_back();
+      return fail(B200_ERR_CUDA, "eig_gen: out of device memory");
+    }
   }
   if (n * n > st->capA) {
     cudaFree(st->dA); cudaFree(st->dW); st->dA = st->dW = nullptr; st->capA = 0;
