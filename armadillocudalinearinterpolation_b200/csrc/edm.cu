@@ -1019,8 +1019,8 @@ __global__ void convert_kernel(const T* __restrict__ in, U* __restrict__ out, si
 // local column k < ncols_pert is u + eps e_{col_begin+k} (one rounded add, as `du(i) += epsilon`),
 // the last local column is u itself (the base evaluation every device repeats).
 __global__ void edm_fd_columns_kernel(const double* __restrict__ u, unsigned n, double eps, unsigned col_begin,
-                                      unsigned ncols_pert, double* __restrict__ z) {
-  const size_t total = (size_t)(ncols_pert + 1) * n;
+                                      unsigned ncols_pert, double* __restrict__ z, unsigned with_base) {
+  const size_t total = (size_t)(ncols_pert + with_base) * n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned k = (unsigned)(i / n), r = (unsigned)(i % n);
     double v = u[r];
@@ -1028,11 +1028,12 @@ __global__ void edm_fd_columns_kernel(const double* __restrict__ u, unsigned n, 
     z[i] = v;
   }
 }
-// jacobian.col(i) = (df - f) * pow(epsilon,-1)  (NewtonSolver.cpp:194, Stability.cpp:108); f = local column ncols_pert
+// jacobian.col(i) = (df - f) * pow(epsilon,-1)  (NewtonSolver.cpp:194, Stability.cpp:108); f = local column ncols_pert,
+// or f0_given when the caller already holds F(u) (NewtonSolver.cpp:110 computes it before the Jacobian)
 __global__ void edm_fd_jacobian_kernel(const double* __restrict__ f, unsigned n, unsigned ncols_pert, double inv_eps,
-                                       double* __restrict__ jac) {
+                                       double* __restrict__ jac, const double* __restrict__ f0_given) {
   const size_t total = (size_t)ncols_pert * n;
-  const double* f0 = f + (size_t)ncols_pert * n;
+  const double* f0 = f0_given ? f0_given : f + (size_t)ncols_pert * n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     jac[i] = __dmul_rn(__dsub_rn(f[i], f0[i % n]), inv_eps);
 }
@@ -1484,7 +1485,7 @@ int exchange_slots(b200_edm* h, cudaStream_t st, size_t slot_bytes, size_t acc_s
 // accept flags are all-gathered and the primary reduces.  Either way the result is bitwise that of one device.
 template <typename T>
 int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, bool fd, double eps, double* out_cols,
-                  double* f0_out) {
+                  double* f0_out, const double* f0_in = nullptr) {
   DeviceScope callers_device(-1);   // the loop below switches devices; the caller gets its own back on every exit
   B200_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
@@ -1496,7 +1497,8 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
   B200_TRY(ensure_pinned(h, 2 * n * (ncols + 1)));     // z / u in, results out (never re-allocated below)
   const bool by_columns = ndev == 1 || ncols >= 4 * ndev;
   const size_t cpd = by_columns ? (ncols + ndev - 1) / ndev : ncols;          // result columns per device slot
-  const size_t nitems_all = (ncols + (fd ? 1 : 0)) * R;
+  const size_t base = (fd && !f0_in) ? 1 : 0;   // the base evaluation F(u) rides along unless the caller already holds it
+  const size_t nitems_all = (ncols + base) * R;
   const size_t per = (nitems_all + ndev - 1) / ndev;                            // item mode: items per device
   h->last_sliced = ndev > 1;
   h->last_pos_external = false;
@@ -1511,7 +1513,7 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
     size_t c_lo = 0, c_hi = ncols;
     if (by_columns) { c_lo = d * cpd < ncols ? d * cpd : ncols; c_hi = (d + 1) * cpd < ncols ? (d + 1) * cpd : ncols; }
     const size_t cols_res = c_hi - c_lo;                       // result columns computed here
-    const size_t cols_loc = cols_res + (fd ? 1 : 0);           // + the base column
+    const size_t cols_loc = cols_res + base;                   // + the base column
     size_t i_lo = 0, i_hi = cols_loc * R;
     if (!by_columns) { i_lo = d * per < nitems_all ? d * per : nitems_all; i_hi = (d + 1) * per < nitems_all ? (d + 1) * per : nitems_all; }
     B200_TRY(ensure_batch(g, cols_loc > cpd + 1 ? cols_loc : cpd + 1, (i_hi - i_lo) ? (i_hi - i_lo) : 1));
@@ -1522,16 +1524,17 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
     {
     NvtxRange nvtx("edm:lift");
     if (fd) {
-      B200_TRY(ensure_u(g, n));
+      B200_TRY(ensure_u(g, 2 * n));                            // u, then the caller's F(u) if given
       if (g->up_pending) { B200_CUDA(cudaEventSynchronize(g->ev_up)); g->up_pending = false; }
       B200_TRY(ensure_pinned(g, 2 * n));
       memcpy(g->h_pin, z_or_u, n * sizeof(double));
-      B200_CUDA(cudaMemcpyAsync(g->d_u, g->h_pin, n * sizeof(double), cudaMemcpyHostToDevice, gs));
+      if (f0_in) memcpy(g->h_pin + n, f0_in, n * sizeof(double));
+      B200_CUDA(cudaMemcpyAsync(g->d_u, g->h_pin, (f0_in ? 2 : 1) * n * sizeof(double), cudaMemcpyHostToDevice, gs));
       B200_CUDA(cudaEventRecord(g->ev_up, gs));
       g->up_pending = true;
       const size_t total = cols_loc * n;
       edm_fd_columns_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, B200_CNT(gs)>>>(
-          g->d_u, (unsigned)n, eps, (unsigned)c_lo, (unsigned)cols_res, g->d_z);
+          g->d_u, (unsigned)n, eps, (unsigned)c_lo, (unsigned)cols_res, g->d_z, (unsigned)base);
       B200_CUDA(cudaGetLastError());
     } else {
       B200_TRY(upload_z(g, z_or_u + c_lo * n, n, cols_loc, gs));
@@ -1553,7 +1556,7 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
         B200_TRY(run_reduce<T>(g, cols_loc, (const T*)g->d_pos, g->d_accept, g->d_f, gs));
         const size_t total = cols_res * n;
         edm_fd_jacobian_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, B200_CNT(gs)>>>(
-            g->d_f, (unsigned)n, (unsigned)cols_res, pow(eps, -1), slot);
+            g->d_f, (unsigned)n, (unsigned)cols_res, pow(eps, -1), slot, f0_in ? g->d_u + n : nullptr);
         B200_CUDA(cudaGetLastError());
       } else {
         B200_TRY(run_reduce<T>(g, cols_loc, (const T*)g->d_pos, g->d_accept, slot, gs));
@@ -1569,11 +1572,11 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
   const double* d_result = (const double*)h->d_gather;
   const double* d_f0 = nullptr;
   if (by_columns) {
-    if (fd) d_f0 = h->d_f + (((cpd < ncols ? cpd : ncols)) * n);     // the primary's base column (local column cols_res)
+    if (base) d_f0 = h->d_f + (((cpd < ncols ? cpd : ncols)) * n);   // the primary's base column (local column cols_res)
   } else {
     // item mode: all positions are here in item order; the usual fixed-order reduction over every column
     NvtxRange nvtx("edm:reduce");
-    B200_TRY(run_reduce<T>(h, ncols + (fd ? 1 : 0), (const T*)h->d_gather, h->d_gather_acc, h->d_f, st));
+    B200_TRY(run_reduce<T>(h, ncols + base, (const T*)h->d_gather, h->d_gather_acc, h->d_f, st));
     if (fd) {
       const size_t total = ncols * n;
       if (total > h->jac_cap) {
@@ -1582,10 +1585,10 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
         h->jac_cap = total;
       }
       edm_fd_jacobian_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, B200_CNT(st)>>>(
-          h->d_f, (unsigned)n, (unsigned)ncols, pow(eps, -1), h->d_jac);
+          h->d_f, (unsigned)n, (unsigned)ncols, pow(eps, -1), h->d_jac, f0_in ? h->d_u + n : nullptr);
       B200_CUDA(cudaGetLastError());
       d_result = h->d_jac;
-      d_f0 = h->d_f + ncols * n;
+      if (base) d_f0 = h->d_f + ncols * n;
     } else {
       d_result = h->d_f;
     }
@@ -1605,7 +1608,8 @@ int compute_multi(b200_edm* h, const double* z_or_u, size_t n, size_t ncols, boo
   h->done_pending = false;
   memcpy(out_cols, h_res, n * ncols * sizeof(double));
   if (f0_out && d_f0) memcpy(f0_out, h->h_pin, n * sizeof(double));
-  h->last_cols = by_columns ? (cpd < ncols ? cpd : ncols) + (fd ? 1 : 0) : ncols + (fd ? 1 : 0);
+  else if (f0_out && f0_in) memcpy(f0_out, f0_in, n * sizeof(double));
+  h->last_cols = by_columns ? (cpd < ncols ? cpd : ncols) + base : ncols + base;
   if (h->timing) {
     float ms = 0.f;
     B200_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1834,6 +1838,18 @@ int b200_edm_compute_dfdu(b200_edm* h, const double* u, size_t n, double eps, do
   // the difference quotients (NewtonSolver.cpp:194) too, next to the columns they belong to
   return h->prec == B200_F64 ? compute_multi<double>(h, u, n, n, true, eps, jac_out, f0_out)
                              : compute_multi<float>(h, u, n, n, true, eps, jac_out, f0_out);
+}
+
+int b200_edm_compute_dfdu_given_f(b200_edm* h, const double* u, size_t n, double eps, const double* f0, double* jac_out) {
+  B200_TRY(check_handle(h, "edm_compute_dfdu_given_f"));
+  if (!u || !f0 || !jac_out) return fail(B200_ERR_INVALID_ARG, "edm_compute_dfdu_given_f: NULL argument");
+  if (n != ndim(h)) return fail(B200_ERR_INVALID_ARG, "vector length %zu != problem dimension %zu", n, ndim(h));
+  if (!(eps != 0.0)) return fail(B200_ERR_INVALID_ARG, "finite-difference epsilon must be non-zero");
+  if (!h->profile_nc && (!(u[0] == u[0]) || u[0] == 0.0 || u[0] + eps == 0.0))
+    return fail(B200_ERR_INVALID_ARG, "wave speed u[0] (and u[0] + eps) must be finite and non-zero");
+  // only the n perturbed columns are evaluated; the difference quotients use the caller's F(u)
+  return h->prec == B200_F64 ? compute_multi<double>(h, u, n, n, true, eps, jac_out, nullptr, f0)
+                             : compute_multi<float>(h, u, n, n, true, eps, jac_out, nullptr, f0);
 }
 
 int b200_edm_evolve_items_dev(b200_edm* h, const double* z_cols, size_t n, size_t ncols,

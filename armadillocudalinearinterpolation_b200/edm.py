@@ -58,10 +58,19 @@ class EventDrivenMap:
         self.SetNewSeed()
 
     # ---- AbstractNonlinearProblemJacobian (AbstractNonlinearProblemJacobian.hpp:11) ----
-    def ComputeDFDU(self, u, eps, return_f0=False):
+    def ComputeDFDU(self, u, eps, return_f0=False, f0=None):
+        """Forward-difference Jacobian, all evaluations in one batch.  f0 = F(u), if the caller already holds it
+        (the residual of a Newton iteration): the base evaluation is then not repeated; same bits."""
         u = np.ascontiguousarray(u, np.float64).ravel()
         n = u.size
         jac = np.empty((n, n), order="F")
+        if f0 is not None:
+            f0 = np.ascontiguousarray(f0, np.float64).ravel()
+            if f0.size != n:
+                raise ValueError("f0 and u differ in length")
+            check(self._L.b200_edm_compute_dfdu_given_f(self._h, _dp(u), C.c_size_t(n), C.c_double(eps), _dp(f0), _dp(jac)))
+            self._last_cols = n
+            return (jac, f0.copy()) if return_f0 else jac
         f0 = np.empty(n)
         check(self._L.b200_edm_compute_dfdu(self._h, _dp(u), C.c_size_t(n), C.c_double(eps), _dp(jac), _dp(f0)))
         self._last_cols = n + 1

@@ -7,14 +7,14 @@ void EventDrivenMapB200::Check(int status, const char* what) const {
 }
 
 EventDrivenMapB200::EventDrivenMapB200(const arma::vec* pParameters, unsigned int noReal)
-    : mpHandle(NULL), mEpsilon(1e-2), mPrint(true) {
+    : mpHandle(NULL), mEpsilon(1e-2), mPrint(true), mNoDevices(1) {
   Check(b200_edm_create(pParameters->memptr(), pParameters->n_elem, noReal, 1024, 3, B200_F64, &mpHandle),
         "EventDrivenMapB200");
 }
 
 EventDrivenMapB200::EventDrivenMapB200(const arma::vec* pParameters, unsigned int noReal,
                                        unsigned int noNeurons, unsigned int noFronts, b200_dtype precision)
-    : mpHandle(NULL), mEpsilon(1e-2), mPrint(true) {
+    : mpHandle(NULL), mEpsilon(1e-2), mPrint(true), mNoDevices(1) {
   Check(b200_edm_create(pParameters->memptr(), pParameters->n_elem, noReal, noNeurons, noFronts, precision, &mpHandle),
         "EventDrivenMapB200");
 }
@@ -34,6 +34,18 @@ void EventDrivenMapB200::ComputeFBatch(const arma::mat& uCols, arma::mat& fCols)
 void EventDrivenMapB200::ComputeDFDU(const arma::vec& u, arma::mat& dfdu) {
   if (dfdu.n_rows != u.n_elem || dfdu.n_cols != u.n_elem) dfdu.set_size(u.n_elem, u.n_elem);
   Check(b200_edm_compute_dfdu(mpHandle, u.memptr(), u.n_elem, mEpsilon, dfdu.memptr(), NULL), "ComputeDFDU");
+}
+
+void EventDrivenMapB200::ComputeFAndDFDU(const arma::vec& u, arma::vec& f, arma::mat& dfdu) {
+  if (dfdu.n_rows != u.n_elem || dfdu.n_cols != u.n_elem) dfdu.set_size(u.n_elem, u.n_elem);
+  f.set_size(u.n_elem);
+  Check(b200_edm_compute_dfdu(mpHandle, u.memptr(), u.n_elem, mEpsilon, dfdu.memptr(), f.memptr()), "ComputeFAndDFDU");
+}
+
+void EventDrivenMapB200::ComputeDFDUGivenF(const arma::vec& u, const arma::vec& f, arma::mat& dfdu) {
+  if (dfdu.n_rows != u.n_elem || dfdu.n_cols != u.n_elem) dfdu.set_size(u.n_elem, u.n_elem);
+  if (f.n_elem != u.n_elem) throw std::invalid_argument("ComputeDFDUGivenF: f and u differ in length");
+  Check(b200_edm_compute_dfdu_given_f(mpHandle, u.memptr(), u.n_elem, mEpsilon, f.memptr(), dfdu.memptr()), "ComputeDFDUGivenF");
 }
 
 void EventDrivenMapB200::PostProcess() { SetNewSeed(); }
@@ -72,6 +84,7 @@ void EventDrivenMapB200::SetProfileMode(unsigned int nCoarse) {
 }
 void EventDrivenMapB200::SetDevices(const int* deviceIds, unsigned int nDevices) {
   Check(b200_edm_set_devices(mpHandle, deviceIds, nDevices), "SetDevices");
+  mNoDevices = nDevices;
 }
 void EventDrivenMapB200::SetDebugFlag(const bool val) {
   Check(b200_edm_set_debug(mpHandle, val ? 1 : 0), "SetDebugFlag");

@@ -13,9 +13,11 @@
 #include <string>
 #include "AbstractNonlinearProblem.hpp"
 #include "AbstractNonlinearProblemJacobian.hpp"
+#include "AbstractNonlinearProblemFused.hpp"
 #include "b200_edm.h"
 
-class EventDrivenMapB200 : public AbstractNonlinearProblem, public AbstractNonlinearProblemJacobian {
+class EventDrivenMapB200 : public AbstractNonlinearProblem, public AbstractNonlinearProblemJacobian,
+                           public AbstractNonlinearProblemFused {
  public:
   // reference signature (EventDrivenMap.cu:57): parameters (p[0] = beta), realisations.
   // Defaults of the reference: 1024 neurons (mNoThreads, :70), noSpikes = 3 fronts
@@ -30,6 +32,12 @@ class EventDrivenMapB200 : public AbstractNonlinearProblem, public AbstractNonli
   void PostProcess();
   // AbstractNonlinearProblemJacobian: forward differences with the epsilon set below
   void ComputeDFDU(const arma::vec& u, arma::mat& dfdu);
+  // AbstractNonlinearProblemFused: the same Jacobian and the base evaluation F(u) it contains, one batch
+  void ComputeFAndDFDU(const arma::vec& u, arma::vec& f, arma::mat& dfdu);
+  void ComputeDFDUGivenF(const arma::vec& u, const arma::vec& f, arma::mat& dfdu);
+  // one GPU: F alone is a quarter of the n = 3 batch -> reuse the residual; several GPUs: F alone and the batch
+  // are both one ring's serial chain -> one batch per iterate (measured: tools/newton_fused_ab.py)
+  bool PrefersOneBatchPerIterate() const { return mNoDevices > 1; }
 
   // reference setters (EventDrivenMap.hpp:27-51)
   void SetTimeHorizon(const float T);
@@ -62,5 +70,6 @@ class EventDrivenMapB200 : public AbstractNonlinearProblem, public AbstractNonli
   b200_edm* mpHandle;
   double mEpsilon;
   bool mPrint;
+  unsigned int mNoDevices;
 };
 #endif

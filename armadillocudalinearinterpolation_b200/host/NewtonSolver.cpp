@@ -7,20 +7,21 @@
 #include "NewtonSolver.hpp"
 #include <cassert>
 #include <cmath>
+#include <cstdlib>
 #include <iostream>
 
 NewtonSolver::NewtonSolver(AbstractNonlinearProblem* pProblem, const arma::vec* pInitialGuess,
                            const ParameterList* pParameterList)
     : mpProblem(pProblem), mpProblemJacobian(NULL), mpInitialGuess(pInitialGuess),
       mpParameterList(pParameterList), mpConvergenceCriterion(NULL), mMaxIterations(0),
-      mPrintOutput(true), mTolerance(0.0) {}
+      mPrintOutput(true), mTolerance(0.0), mFuse(true) {}
 
 NewtonSolver::NewtonSolver(AbstractNonlinearProblem* pProblem,
                            AbstractNonlinearProblemJacobian* pProblemJacobian,
                            const arma::vec* pInitialGuess, const ParameterList* pParameterList)
     : mpProblem(pProblem), mpProblemJacobian(pProblemJacobian), mpInitialGuess(pInitialGuess),
       mpParameterList(pParameterList), mpConvergenceCriterion(NULL), mMaxIterations(0),
-      mPrintOutput(true), mTolerance(0.0) {}
+      mPrintOutput(true), mTolerance(0.0), mFuse(true) {}
 
 NewtonSolver::~NewtonSolver() { delete mpConvergenceCriterion; }
 
@@ -41,8 +42,21 @@ void NewtonSolver::Solve(arma::vec& solution, arma::vec& residualHistory, ExitFl
   assert(n == (int)solution.n_rows);
   solution = *mpInitialGuess;
 
+  // One object behind both interfaces that implements AbstractNonlinearProblemFused (EventDrivenMapB200): do not
+  // evaluate F(u) twice per iteration.  Either the Jacobian is formed from the residual already in hand, or — when
+  // the problem prefers it — F and dF/dU of every new iterate come in one batch (the Jacobian of an iterate that
+  // turns out to be converged is then computed in vain).  `jacobian` stays the last Jacobian a step was taken with,
+  // as in the reference (pJacobianExternal below).
+  AbstractNonlinearProblemFused* fused = NULL;
+  if (mFuse && mpProblemJacobian && !std::getenv("B200_NEWTON_NO_FUSE") &&
+      dynamic_cast<void*>(mpProblem) == dynamic_cast<void*>(mpProblemJacobian))
+    fused = dynamic_cast<AbstractNonlinearProblemFused*>(mpProblemJacobian);
+  const bool oneBatch = fused && fused->PrefersOneBatchPerIterate();
+
   arma::vec residual(n);
-  mpProblem->ComputeF(solution, residual);
+  arma::mat jacobian(n, n), jacobianAhead;
+  if (oneBatch) { jacobianAhead.set_size(n, n); fused->ComputeFAndDFDU(solution, residual, jacobianAhead); }
+  else mpProblem->ComputeF(solution, residual);
   double residualNorm = arma::norm(residual, 2);
 
   int iteration = 0;
@@ -51,9 +65,10 @@ void NewtonSolver::Solve(arma::vec& solution, arma::vec& residualHistory, ExitFl
   if (mPrintOutput) PrintIteration(iteration, residualNorm, true);
 
   bool converged = mpConvergenceCriterion->TestConvergence(residualNorm);
-  arma::mat jacobian(n, n);
   while (iteration < mMaxIterations && !converged) {
-    if (mpProblemJacobian) mpProblemJacobian->ComputeDFDU(solution, jacobian);
+    if (oneBatch) jacobian = jacobianAhead;
+    else if (fused) fused->ComputeDFDUGivenF(solution, residual, jacobian);
+    else if (mpProblemJacobian) mpProblemJacobian->ComputeDFDU(solution, jacobian);
     else ComputeDFDU(solution, residual, jacobian);
 
     arma::vec direction;
@@ -64,7 +79,8 @@ void NewtonSolver::Solve(arma::vec& solution, arma::vec& residualHistory, ExitFl
     solution += mpParameterList->damping * direction;
     iteration++;
 
-    mpProblem->ComputeF(solution, residual);
+    if (oneBatch) fused->ComputeFAndDFDU(solution, residual, jacobianAhead);
+    else mpProblem->ComputeF(solution, residual);
     residualNorm = arma::norm(residual, 2);
     converged = mpConvergenceCriterion->TestConvergence(residualNorm);
     residualHistory(iteration) = residualNorm;

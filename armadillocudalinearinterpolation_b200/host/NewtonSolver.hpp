@@ -5,6 +5,7 @@
 #include <armadillo>
 #include "AbstractNonlinearProblem.hpp"
 #include "AbstractNonlinearProblemJacobian.hpp"
+#include "AbstractNonlinearProblemFused.hpp"
 #include "AbstractNonlinearSolver.hpp"
 #include "ConvergenceCriterion.hpp"
 
@@ -36,6 +37,9 @@ class NewtonSolver : public AbstractNonlinearSolver {
   void SetProblem(AbstractNonlinearProblem* pProblem);
   void SetProblemJacobian(AbstractNonlinearProblemJacobian* pProblemJacobian);
   void PostProcess();
+  // addition: when problem and Jacobian are ONE object that also implements AbstractNonlinearProblemFused, F(u) is not
+  // evaluated twice per iteration (see that header; default on; off = the reference's call sequence)
+  void SetFusedEvaluation(bool on) { mFuse = on; }
 
  private:
   NewtonSolver();
@@ -51,5 +55,6 @@ class NewtonSolver : public AbstractNonlinearSolver {
   int mMaxIterations;
   bool mPrintOutput;
   double mTolerance;
+  bool mFuse;
 };
 #endif

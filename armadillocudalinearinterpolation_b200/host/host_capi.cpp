@@ -30,6 +30,24 @@ class QuadraticProblem : public AbstractNonlinearProblem, public AbstractNonline
   }
 };
 
+// the same problem offering F and dF/dU in one call (AbstractNonlinearProblemFused): `fused` counts those calls
+class QuadraticProblemFused : public QuadraticProblem, public AbstractNonlinearProblemFused {
+ public:
+  int fused = 0, given = 0;
+  bool oneBatch = true;
+  void ComputeFAndDFDU(const arma::vec& u, arma::vec& f, arma::mat& J) {
+    QuadraticProblem::ComputeF(u, f); --calls;
+    QuadraticProblem::ComputeDFDU(u, J);
+    ++fused;
+  }
+  void ComputeDFDUGivenF(const arma::vec& u, const arma::vec& f, arma::mat& J) {
+    (void)f;
+    QuadraticProblem::ComputeDFDU(u, J);
+    ++given;
+  }
+  bool PrefersOneBatchPerIterate() const { return oneBatch; }
+};
+
 // Linear map problem F(u) = A u - u with user matrix A (for the Stability tests)
 class LinearProblem : public AbstractNonlinearProblem {
  public:
@@ -42,18 +60,24 @@ extern "C" {
 
 const char* b200_host_last_error() { return g_err.c_str(); }
 
-// Newton on the analytic problem.  use_jacobian: 0 = solver's finite differences, 1 = analytic.
+// Newton on the analytic problem.  use_jacobian: 0 = solver's finite differences, 1 = analytic, 2 / 3 = analytic through
+// AbstractNonlinearProblemFused, one batch per iterate / Jacobian given the residual (f_calls then = plain ComputeF
+// calls + 1000 * fused calls + 1000000 * given-F calls).
 // out: solution[n], history[max_it+1] (NaN padded), returns iterations*4 + converged*2 + post_called
 int b200_host_newton_quadratic(int n, const double* guess, double tol, int max_it, double eps, double damping,
                                int use_jacobian, double* solution, double* history, int* n_history,
                                int* f_calls, double* jac_out) {
   try {
-    QuadraticProblem prob;
+    QuadraticProblemFused prob_fused;
+    QuadraticProblem prob_plain;
+    prob_fused.oneBatch = use_jacobian == 2;
+    QuadraticProblem& prob = use_jacobian >= 2 ? static_cast<QuadraticProblem&>(prob_fused) : prob_plain;
     arma::vec g(n), sol(n), hist;
     for (int i = 0; i < n; ++i) g(i) = guess[i];
     NewtonSolver::ParameterList pars;
     pars.printOutput = false;
-    NewtonSolver* solver = use_jacobian ? new NewtonSolver(&prob, &prob, &g, &pars) : new NewtonSolver(&prob, &g, &pars);
+    NewtonSolver* solver = use_jacobian >= 2 ? new NewtonSolver(&prob_fused, &prob_fused, &g, &pars)
+                         : use_jacobian ? new NewtonSolver(&prob, &prob, &g, &pars) : new NewtonSolver(&prob, &g, &pars);
     // edits after construction must apply (Driver.cu:37)
     pars.tolerance = tol; pars.maxIterations = max_it; pars.finiteDifferenceEpsilon = eps; pars.damping = damping;
     AbstractNonlinearSolver::ExitFlagType flag;
@@ -63,7 +87,7 @@ int b200_host_newton_quadratic(int n, const double* guess, double tol, int max_i
     for (int i = 0; i < n; ++i) solution[i] = sol(i);
     *n_history = (int)hist.n_elem;
     for (arma::uword i = 0; i < hist.n_elem; ++i) history[i] = hist(i);
-    *f_calls = prob.calls;
+    *f_calls = prob.calls + 1000 * prob_fused.fused + 1000000 * prob_fused.given;
     if (jac_out) std::memcpy(jac_out, J.memptr(), sizeof(double) * n * n);
     return ((int)hist.n_elem - 1) * 4 + (flag == AbstractNonlinearSolver::ExitFlagType::converged ? 2 : 0) + (prob.post == 1 ? 1 : 0);
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
@@ -119,6 +143,7 @@ int b200_host_edm_newton(double beta, unsigned R, unsigned N, const double* gues
     NewtonSolver::ParameterList pars;
     pars.tolerance = tol; pars.maxIterations = max_it; pars.printOutput = false; pars.finiteDifferenceEpsilon = eps;
     NewtonSolver* solver = mode ? new NewtonSolver(&map, &map, &g, &pars) : new NewtonSolver(&map, &g, &pars);
+    if (mode == 3) solver->SetFusedEvaluation(false);   // plug-in Jacobian with the reference's call sequence (F, then dF/dU)
     AbstractNonlinearSolver::ExitFlagType flag;
     arma::mat J(n, n);
     solver->Solve(sol, hist, flag, &J);
@@ -171,6 +196,7 @@ int b200_host_edm_newton_multi(double beta, unsigned R, unsigned N, const double
     NewtonSolver::ParameterList pars;
     pars.tolerance = tol; pars.maxIterations = max_it; pars.printOutput = false; pars.damping = 1.0;
     NewtonSolver* solver = mode ? new NewtonSolver(&map, &map, &g, &pars) : new NewtonSolver(&map, &g, &pars);
+    if (mode == 3) solver->SetFusedEvaluation(false);
     pars.finiteDifferenceEpsilon = eps;      // set after construction, as Driver.cu:37
     AbstractNonlinearSolver::ExitFlagType flag;
     arma::mat J(n, n);

@@ -630,26 +630,34 @@ def main():
                 dp = lambda a: a.ctypes.data_as(C.c_void_p)
                 dev_sets = [1] + ([n_gpus] if n_gpus > 1 else [])
 
-                def newton(ndev):
+                def newton(ndev, mode=1):
                     sol = np.zeros(3); hist = np.full(11, np.nan); nh = C.c_int(); J = np.zeros((3, 3), order="F"); msv = np.zeros(2)
                     devs = (C.c_int * ndev)(*range(ndev))
                     rc = host.b200_host_edm_newton_multi(C.c_double(BETA), 1000, 1024, dp(Z_DRIVER), 3, C.c_double(1e-4), 10,
-                                                         C.c_double(1e-2), 1, C.c_double(0.0), ndev, devs, dp(sol), dp(hist),
+                                                         C.c_double(1e-2), mode, C.c_double(0.0), ndev, devs, dp(sol), dp(hist),
                                                          C.byref(nh), dp(J), dp(msv))
                     if rc < 0:
                         raise RuntimeError(host.b200_host_last_error().decode())
                     return rc, sol, hist[:nh.value], J, msv
 
                 res = {nd: newton(nd) for nd in dev_sets}
+                # mode 3: the reference's call sequence (ComputeF after the update, ComputeDFDU — which repeats F — on the
+                # next turn) instead of one batched F + dF/dU per iterate; same iterates
+                res_seq = {nd: newton(nd, 3) for nd in dev_sets}
                 r1 = res[1]
                 cpp["newton_config4_R1000_N1024"] = {
                     "driver_settings": "Driver.cu:28-37 (tol 1e-4, <= 10 iterations, FD eps 1e-2), Jacobian through ComputeDFDU",
                     "converged": bool(r1[0] == 1), "iterations": int(len(r1[2]) - 1), "solution": r1[1].tolist(),
                     "final_residual": float(r1[2][-1]),
                     "solve_ms": {str(nd): float(res[nd][4][0]) for nd in dev_sets},
+                    "solve_ms_reference_call_sequence": {str(nd): float(res_seq[nd][4][0]) for nd in dev_sets},
+                    "evaluation": "F(u) never evaluated twice per iteration (AbstractNonlinearProblemFused): one GPU — Jacobian from the residual in hand (n evaluations); several GPUs — F and dF/dU of every iterate in one batch",
                     "jacobian_ms": {str(nd): float(res[nd][4][1]) for nd in dev_sets},
                     "bitwise_equal_across_device_counts": all(
                         np.array_equal(res[nd][1], r1[1]) and np.array_equal(res[nd][2], r1[2]) and np.array_equal(res[nd][3], r1[3])
+                        for nd in dev_sets),
+                    "bitwise_equal_to_reference_call_sequence": all(
+                        np.array_equal(res_seq[nd][1], r1[1]) and np.array_equal(res_seq[nd][2], r1[2]) and np.array_equal(res_seq[nd][3], r1[3])
                         for nd in dev_sets)}
 
                 def stability(R, ndev):

@@ -93,6 +93,12 @@ int b200_edm_compute_f_batch(b200_edm* h, const double* z_cols, size_t n, size_t
  * f0_out (nullable) receives F(u). jac is n x n column-major. */
 int b200_edm_compute_dfdu(b200_edm* h, const double* u, size_t n, double eps,
                           double* jac_out, double* f0_out);
+/* The same Jacobian when the caller already holds f0 = F(u) — NewtonSolver.cpp:110 evaluates the residual before
+ * :93 / :191 ask for the Jacobian, which then repeats it: only the n perturbed columns are evaluated here and
+ * J(:,i) = (F(u + eps e_i) - f0) * pow(eps,-1).  With f0 = b200_edm_compute_f(u) the result is bitwise that of
+ * b200_edm_compute_dfdu. */
+int b200_edm_compute_dfdu_given_f(b200_edm* h, const double* u, size_t n, double eps,
+                                  const double* f0, double* jac_out);
 
 /* ---- profile map (BASELINE config 5: "1e3-dim coarse profile"; NEW, not in the reference) ----
  * The reference's coarse variable is 3 numbers (wave speed + front delays, noSpikes in

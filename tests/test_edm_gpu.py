@@ -122,6 +122,11 @@ def test_jacobian_matches_oracle_and_column_loop(b200, oracle):
         assert np.array_equal(J[:, i], (m.ComputeF(du) - f0) * eps ** -1)
     gj = GOLD["jacobian_driver_N1024"]
     assert np.max(np.abs(J - np.array(gj["J"]))) < 1e-8 * np.max(np.abs(gj["J"]))
+    # the Jacobian from a residual already in hand (what NewtonSolver.cpp:110 computed before :93 asks): same bits,
+    # n evaluations instead of n + 1
+    assert np.array_equal(m.ComputeDFDU(Z_DRIVER, eps, f0=m.ComputeF(Z_DRIVER)), J)
+    with pytest.raises(ValueError):
+        m.ComputeDFDU(Z_DRIVER, eps, f0=np.zeros(2))
 
 
 def test_batch_and_sharded_items_are_bitwise_identical(b200):
@@ -224,6 +229,11 @@ def test_in_process_multi_device_is_bitwise_single_device(b200):
     assert np.array_equal(Ja, Jb) and np.array_equal(fa, fb)
     uc = np.stack([u * (1 + 1e-3 * k) for k in range(40)], axis=1)
     assert np.array_equal(a.ComputeFBatch(uc), b.ComputeFBatch(uc))
+    # the Jacobian from a residual already in hand (b200_edm_compute_dfdu_given_f): item mode and column mode
+    c = make_map(b200, dict(R=37, N=512, sigma=0.4, seed=5)); c.SetDevices(devs)
+    Jc, fc = c.ComputeDFDU(Z_DRIVER, 1e-2, return_f0=True)
+    assert np.array_equal(c.ComputeDFDU(Z_DRIVER, 1e-2, f0=fc), Jc)
+    assert np.array_equal(b.ComputeDFDU(u, 1e-3, f0=fb), Jb)
     # the library hands the caller's current device back, whichever device it was (the map lives on device 0)
     import torch
     torch.cuda.set_device(n_dev - 1)

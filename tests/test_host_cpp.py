@@ -53,6 +53,15 @@ def test_newton_converges_quadratically_and_counts_calls(host):
     rj = newton_quadratic(host, [1.0, 1.0, 1.0], use_jac=1)                  # user Jacobian: 1 + its evaluations
     assert rj["calls"] == 1 + rj["its"] and np.allclose(rj["sol"], u, atol=1e-9)
     assert np.allclose(rj["J"], r["J"], atol=1e-5)                           # pJacobianExternal hands out the last Jacobian
+    # a problem that offers F and dF/dU in one call (AbstractNonlinearProblemFused): one fused call per iterate, no
+    # plain ComputeF at all; same iterates, and the Jacobian handed out is still the last one a step was taken with
+    rf = newton_quadratic(host, [1.0, 1.0, 1.0], use_jac=2)
+    assert rf["calls"] == 1000 * (1 + rf["its"]) and rf["its"] == rj["its"] and rf["post_once"]
+    assert np.array_equal(rf["sol"], rj["sol"]) and np.array_equal(rf["hist"], rj["hist"]) and np.array_equal(rf["J"], rj["J"])
+    # ... or the Jacobian from the residual in hand: 1 + its plain evaluations, one given-F Jacobian per iteration
+    rg = newton_quadratic(host, [1.0, 1.0, 1.0], use_jac=3)
+    assert rg["calls"] == (1 + rg["its"]) + 1000000 * rg["its"] and rg["its"] == rj["its"]
+    assert np.array_equal(rg["sol"], rj["sol"]) and np.array_equal(rg["hist"], rj["hist"]) and np.array_equal(rg["J"], rj["J"])
 
 
 def test_newton_not_converged_and_damping(host):
@@ -114,14 +123,15 @@ def test_edm_newton_through_the_reference_interfaces(host, oracle):
     fixed point the oracle's Newton finds (Driver.cu settings: tol 1e-4, eps 1e-2, <= 10 iterations)."""
     R, N, n = 8, 1024, 3
     res = []
-    for mode in (0, 1):
+    for mode in (0, 1, 3):   # 3: plug-in Jacobian with the reference's call sequence (F, then dF/dU) instead of the fused one
         sol = np.zeros(n); hist = np.full(11, np.nan); nh = C.c_int(); J = np.zeros((n, n), order="F")
         rc = host.b200_host_edm_newton(C.c_double(BETA), R, N, dp(Z_DRIVER), n, C.c_double(1e-4), 10, C.c_double(1e-2),
                                        mode, C.c_double(0.0), dp(sol), dp(hist), C.byref(nh), dp(J))
         assert rc >= 0, host.b200_host_last_error()
         res.append((rc, sol, hist[:nh.value], J))
-    assert res[0][0] == 1 and res[1][0] == 1
-    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][3], res[1][3])
+    assert res[0][0] == 1 and res[1][0] == 1 and res[2][0] == 1
+    for other in (res[1], res[2]):
+        assert np.array_equal(res[0][1], other[1]) and np.array_equal(res[0][2], other[2]) and np.array_equal(res[0][3], other[3])
     # oracle Newton with the same settings
     cfg = oracle.edm_cfg(R=1, N=N)
     z = Z_DRIVER.copy(); f, _ = oracle.edm_compute_f(cfg, z, aux=False); hist = [np.linalg.norm(f)]

@@ -85,6 +85,7 @@ def test_gpu_profile_jacobian_and_mode_switch(b200, oracle):
         du = u.copy(); du[i] += 1e-3
         fi, _ = oracle.profile_compute_f(cfg, nc, du)
         assert np.max(np.abs(J[:, i] - (fi - fo) / 1e-3)) < 1e-6 * max(1.0, np.max(np.abs(J[:, i])))
+    assert np.array_equal(m.ComputeDFDU(u, 1e-3, f0=m.ComputeF(u)), J)     # given-F form: same bits
     with pytest.raises(b200.B200Error):
         m.ComputeF(Z_DRIVER)                     # wrong length in profile mode
     m.SetProfileMode(0)                          # back to the reference's front map
