@@ -43,3 +43,15 @@ if which == "edm1":     # ONE ring alone: the serial event chain without content
     m = B.EventDrivenMap([bench.BETA], 1, noNeurons=1024)
     for _ in range(3):
         print(m.ComputeF(bench.Z_DRIVER))
+if which == "interp2s":   # cell-sorted queries: the straight-line affine / tile kernel serves the call
+    plan = B.Interp2Plan(*bench.make_grid())
+    g = torch.Generator(device="cuda").manual_seed(2235)
+    xq = torch.rand(bench.NQ, generator=g, device="cuda", dtype=torch.float64)
+    yq = torch.rand(bench.NQ, generator=g, device="cuda", dtype=torch.float64)
+    cell = (xq * 4095).floor().to(torch.int64) * 4096 + (yq * 4095).floor().to(torch.int64)
+    o = cell.argsort(); del cell
+    xq, yq = xq[o].contiguous(), yq[o].contiguous(); del o
+    zq = torch.empty_like(xq)
+    for _ in range(3):
+        plan.scattered(xq, yq, out=zq)
+    torch.cuda.synchronize()
