@@ -6,6 +6,8 @@ code = r'''
 import sys, os
 sys.path.insert(0, %r)
 import numpy as np, torch
+from armadillocudalinearinterpolation_b200 import _lib
+if os.environ.get("B200_AB_LIB"): _lib.LIB_PATH = os.environ["B200_AB_LIB"]   # A/B of another build of the library
 import armadillocudalinearinterpolation_b200 as B, bench
 grid = bench.make_grid()
 g2 = torch.Generator(device="cuda").manual_seed(2236)
