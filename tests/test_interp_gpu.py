@@ -474,3 +474,32 @@ def test_interp2_locality_probe_both_kernels_same_bits(b200, oracle, y_first, mo
             zq = plan.scattered(tx, ty, extrap=2.5)
             torch.cuda.synchronize()
             assert same_bits(zq.cpu().numpy(), ref[idx])
+
+
+def test_plans_run_on_their_own_device_and_restore_the_callers(b200, oracle):
+    """A plan lives on the device that was current when it was created; host-buffer calls made while ANOTHER device is
+    current still run there (same bits) and hand the caller's current device back."""
+    import torch
+    if b200.device_count() < 2:
+        pytest.skip("needs at least two GPUs in this process")
+    rng = np.random.default_rng(31)
+    x = np.sort(rng.random(300)); y = np.sort(rng.random(200)); z = rng.standard_normal((200, 300))
+    xq = rng.random(50_000) * 1.1 - 0.05; yq = rng.random(50_000) * 1.1 - 0.05
+    torch.cuda.set_device(0)
+    p2 = b200.Interp2Plan(x, y, z)
+    p1 = b200.Interp1Plan(x, z[0])
+    ref2 = oracle.interp2_scattered(x, y, z, xq, yq, extrap=3.0)
+    ref1 = oracle.interp1(x, z[0], xq, extrap=3.0, want_idx=False)
+    last = b200.device_count() - 1
+    torch.cuda.set_device(last)
+    try:
+        assert same_bits(p2.scattered(xq, yq, extrap=3.0), ref2)
+        assert torch.cuda.current_device() == last
+        assert same_bits(p1(xq, extrap=3.0), ref1)
+        assert torch.cuda.current_device() == last
+        zi = p2.grid(xq[:64].copy(), yq[:32].copy(), extrap=3.0)
+        assert same_bits(zi, oracle.interp2_grid(x, y, z, xq[:64], yq[:32], extrap=3.0))
+        p1.close(); p2.close()
+        assert torch.cuda.current_device() == last
+    finally:
+        torch.cuda.set_device(0)
