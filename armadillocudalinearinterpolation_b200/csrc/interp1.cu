@@ -135,6 +135,11 @@ __global__ void __launch_bounds__(kThreads)
 interp1_vec_kernel(AxisDev<T> ax, const T* __restrict__ seg, const BinRec<T>* __restrict__ rec,
                    const T* __restrict__ xi, T* __restrict__ yi, int32_t* __restrict__ idx, size_t nvec, T extrap) {
   constexpr int V = Vec256<T>::n;
+  // programmatic dependent launch (plan1_launch): this grid may have been scheduled while the previous kernel of
+  // the stream was still draining; nothing is read or written before that kernel has completed and flushed
+  // (a no-op for an ordinary launch), and the next launch of the stream may be scheduled from now on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
   const auto ld = make_loader1<T>(seg);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -343,8 +348,19 @@ int plan1_launch(b200_interp1_plan* p, const T* xi, size_t ni, T* yi, int32_t* i
     const size_t mult = forced ? forced : (blocks > (size_t)148 * 256 ? 64 : 16);
     int grid = (int)(blocks < (size_t)148 * mult ? blocks : (size_t)148 * mult);
     const BinRec<T>* rec = (const BinRec<T>*)p->binrec;
-    if (idx) interp1_vec_kernel<T, true><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, rec, xi, yi, idx, nvec, extrap);
-    else interp1_vec_kernel<T, false><<<grid, kThreads, 0, B200_CNT(st)>>>(ax, seg, rec, xi, yi, nullptr, nvec, extrap);
+    // back-to-back calls on one stream (a caller that batches, the chunks of the host-buffer pipeline): with the
+    // programmatic-stream-serialization attribute the next grid is scheduled while this one drains and starts the
+    // moment it has completed — no launch bubble between 30-60 us kernels.  B200_INTERP1_PDL=0: ordinary launches.
+    static const bool pdl = [] { const char* e = getenv("B200_INTERP1_PDL"); return !(e && atoi(e) == 0); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = B200_CNT(st);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    int32_t* no_idx = nullptr;
+    if (idx) B200_CUDA(cudaLaunchKernelEx(&cfg, interp1_vec_kernel<T, true>, ax, seg, rec, xi, yi, idx, nvec, extrap));
+    else B200_CUDA(cudaLaunchKernelEx(&cfg, interp1_vec_kernel<T, false>, ax, seg, rec, xi, yi, no_idx, nvec, extrap));
   }
   size_t done = nvec * V;
   if (done < ni) {

@@ -1,6 +1,6 @@
 """interp1 at BASELINE configs[0] size (1e6 knots, 1e7 queries), 8 rotating buffer pairs as in bench.py:
 uniform / non-uniform knots x sorted / unsorted queries, for a sweep of launch shapes (B200_INTERP1_GRID_MULT)
-and with / without the bin records (B200_INTERP1_BINREC).  One subprocess per setting (the env is read once)."""
+and with / without programmatic dependent launch (B200_INTERP1_PDL).  One subprocess per setting (the env is read once)."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
@@ -32,7 +32,7 @@ for kind in ("uniform", "nonuniform"):
     p1.close()
 print("  ".join(res))
 ''' % ROOT
-settings = [dict(B200_INTERP1_BINREC="0"), dict()] + [dict(B200_INTERP1_GRID_MULT=str(m)) for m in (4, 8, 12, 24, 32, 64)]
+settings = [dict(B200_INTERP1_PDL="0"), dict(B200_INTERP1_PDL="1")] + [dict(B200_INTERP1_GRID_MULT=str(m)) for m in (4, 8, 12, 24, 32, 64)]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     settings = settings[:2]
 for st in settings:
