@@ -503,3 +503,43 @@ def test_plans_run_on_their_own_device_and_restore_the_callers(b200, oracle):
         assert torch.cuda.current_device() == last
     finally:
         torch.cuda.set_device(0)
+
+
+def test_device_paths_capture_into_a_cuda_graph(b200, oracle):
+    """The device-pointer entry points make no host round trip and allocate nothing after a first call of the same
+    shape, so a caller can capture them into a CUDA graph (torch.cuda.CUDAGraph) and replay it on new data:
+    interp1 (programmatic dependent launch), interp2 scattered (both kernels of the locality decision) and the
+    tensor grid; every replay is bitwise the direct call."""
+    import torch
+    rng = np.random.default_rng(77)
+    n = 1 << 21                                                   # >= 2^20: the scattered call launches both kernels
+    x = np.linspace(0.0, 1.0, 700); y = np.linspace(-1.0, 1.0, 500); z = rng.standard_normal((500, 700))
+    xg = np.sort(rng.random(5000)); yg = rng.standard_normal(5000)
+    p2 = b200.Interp2Plan(x, y, z); p1 = b200.Interp1Plan(xg, yg)
+    xq = torch.rand(n, device="cuda", dtype=torch.float64); yq = torch.rand(n, device="cuda", dtype=torch.float64) * 2 - 1
+    q1 = torch.rand(n, device="cuda", dtype=torch.float64)
+    xi = torch.rand(96, device="cuda", dtype=torch.float64).sort().values
+    yi = (torch.rand(64, device="cuda", dtype=torch.float64) * 2 - 1).sort().values
+    zq = torch.empty_like(xq); y1 = torch.empty_like(q1)
+    for _ in range(2):                                            # first calls: allocations, function attributes
+        p2.scattered(xq, yq, out=zq); p1(q1, out=y1); zi = p2.grid(xi, yi)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        p2.scattered(xq, yq, out=zq)
+        p1(q1, out=y1)
+        p1(q1, out=y1)                                            # back to back: the programmatic edge
+        zi = p2.grid(xi, yi)
+    for seed in (1, 2):
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        xq.copy_(torch.rand(n, generator=gen, device="cuda", dtype=torch.float64))
+        yq.copy_(torch.rand(n, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1)
+        q1.copy_(torch.rand(n, generator=gen, device="cuda", dtype=torch.float64))
+        if seed == 2:                                             # sorted by cell: the replay takes the other kernel
+            o = ((xq * 699).floor() * 500 + ((yq + 1) / 2 * 499).floor()).argsort()
+            xq.copy_(xq[o]); yq.copy_(yq[o])
+        g.replay()
+        torch.cuda.synchronize()
+        assert same_bits(zq.cpu().numpy(), oracle.interp2_scattered(x, y, z, xq.cpu().numpy(), yq.cpu().numpy(), nthreads=8))
+        assert same_bits(y1.cpu().numpy(), oracle.interp1(xg, yg, q1.cpu().numpy(), want_idx=False, nthreads=8))
+        assert same_bits(zi.cpu().numpy(), oracle.interp2_grid(x, y, z, xi.cpu().numpy(), yi.cpu().numpy()))
