@@ -350,3 +350,36 @@ def test_config5_profile_stability_cpp(host, b200):
     if ndev >= 2:
         cnt2, J2, lam2, ms2 = _profile_stability(host, R, N, nc, T, u, eps, min(ndev, 8))
         assert cnt2 == cnt and np.array_equal(J2, J)
+
+
+@pytest.mark.gpu
+def test_config5_rest_state_known_spectrum_cpp(host, b200):
+    """BASELINE config 5 at its full shape (n = 1000 coarse unknowns, N = 1024 neurons) on a state whose answer is
+    known in closed form: at rest (v = I below threshold, s = 0) no neuron fires, the map is linear,
+        v(T) = v e^-T + I (1 - e^-T) + kappa s,   s(T) = s e^-(beta T),   kappa = e^-T (e^((1-beta) T) - 1) / (1 - beta),
+    so with M = restrict o lift (linear interpolation coarse -> fine -> coarse, rows sum to one)
+        I + J = [[e^-T M, kappa M], [0, e^-(beta T) M]].
+    Checked through Stability::ComputeNumUnstableEigenvalues of the C++ host layer (FD Jacobian on the GPU, eig_gen =
+    cuSOLVER GEEV behind the shim): the block relations, the spectrum against the two 500 x 500 blocks, the largest
+    eigenvalue e^-T (constant profiles), and zero unstable eigenvalues."""
+    nc, N, T, eps = 500, 1024, 1.0, 1e-3
+    beta = float(np.float32(13.0589)); I = float(np.float32(0.9))
+    u = np.concatenate([np.full(nc, I), np.zeros(nc)])
+    cnt, J, lam, ms = _profile_stability(host, 1, N, nc, T, u, eps, 1)
+    assert cnt == 0
+    A = J + np.eye(2 * nc)
+    e1, eb = np.exp(-T), np.exp(-beta * T)
+    kappa = e1 * (np.exp((1.0 - beta) * T) - 1.0) / (1.0 - beta)
+    M = A[nc:, nc:] / eb
+    assert np.allclose(M.sum(axis=1), 1.0, atol=1e-6)                       # interpolation reproduces constants
+    assert np.max(np.abs(A[:nc, :nc] - e1 * M)) < 1e-9                      # dv(T)/dv
+    assert np.max(np.abs(A[:nc, nc:] - kappa * M)) < 1e-9                   # dv(T)/ds
+    assert np.max(np.abs(A[nc:, :nc])) < 1e-9                               # ds(T)/dv = 0
+    mu = np.linalg.eigvals(M)
+    ref = np.concatenate([e1 * mu, eb * mu])
+    assert np.allclose(np.sort(np.abs(lam)), np.sort(np.abs(ref)), atol=1e-8)
+    assert abs(np.max(np.abs(lam)) - e1) < 1e-8                             # the constant profile decays like e^-T
+    ndev = b200.device_count()
+    if ndev >= 2:
+        cnt2, J2, lam2, _ = _profile_stability(host, 1, N, nc, T, u, eps, min(ndev, 8))
+        assert cnt2 == 0 and np.array_equal(J2, J)
