@@ -262,6 +262,39 @@ int b200_host_profile_stability(double beta, unsigned R, unsigned N, unsigned n_
   } catch (const std::exception& e) { g_err = e.what(); return -1000; }
 }
 
+// NewtonSolver on the PROFILE map (n = 2 n_coarse unknowns): u -> a zero of Phi_T(u) - u, Jacobian through the
+// plug-in (one batch of n or n + 1 evaluations per iteration, over `ndev` devices).  Returns 1 converged, 0 not,
+// -1 error; history[max_it + 1].
+int b200_host_profile_newton(double beta, unsigned R, unsigned N, unsigned n_coarse, double T, const double* guess,
+                             double tol, int max_it, double eps, int ndev, const int* devs, double* solution,
+                             double* history, int* n_history, double* ms_out) {
+  try {
+    arma::vec p(1);
+    p(0) = beta;
+    const int n = 2 * (int)n_coarse;
+    EventDrivenMapB200 map(&p, R, N, 3);
+    map.SetPrintOutput(false);
+    map.SetTimeHorizon((float)T);
+    map.SetProfileMode(n_coarse);
+    map.SetFiniteDifferenceEpsilon(eps);
+    if (ndev > 1) map.SetDevices(devs, (unsigned)ndev);
+    arma::vec g(n), sol(n), hist;
+    for (int i = 0; i < n; ++i) g(i) = guess[i];
+    NewtonSolver::ParameterList pars;
+    pars.tolerance = tol; pars.maxIterations = max_it; pars.printOutput = false; pars.finiteDifferenceEpsilon = eps;
+    NewtonSolver solver(&map, &map, &g, &pars);
+    AbstractNonlinearSolver::ExitFlagType flag;
+    auto t0 = std::chrono::steady_clock::now();
+    solver.Solve(sol, hist, flag);
+    auto t1 = std::chrono::steady_clock::now();
+    if (ms_out) ms_out[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    for (int i = 0; i < n; ++i) solution[i] = sol(i);
+    *n_history = (int)hist.n_elem;
+    for (arma::uword i = 0; i < hist.n_elem; ++i) history[i] = hist(i);
+    return flag == AbstractNonlinearSolver::ExitFlagType::converged ? 1 : 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // arma::eig_gen as the host layer sees it (cuSOLVER behind the shim for n >= 256, own QR below / on request)
 int b200_host_eig_gen(int n, const double* A_colmajor, double* eig_re, double* eig_im, double* ms_out) {
   try {

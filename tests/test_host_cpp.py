@@ -383,3 +383,33 @@ def test_config5_rest_state_known_spectrum_cpp(host, b200):
     if ndev >= 2:
         cnt2, J2, lam2, _ = _profile_stability(host, 1, N, nc, T, u, eps, min(ndev, 8))
         assert cnt2 == 0 and np.array_equal(J2, J)
+
+
+@pytest.mark.gpu
+def test_newton_on_the_profile_map_finds_the_rest_state(host, b200):
+    """NewtonSolver on the profile map (n = 2 n_coarse unknowns, Jacobian = one batch of evaluations through the
+    plug-in).  The travelling wave is not a fixed point of this map in the lab frame; the rest state
+    v = I, s = 0 is.  From a smooth sub-threshold perturbation nobody fires, the map is linear and Newton lands on
+    the rest state in one step (200 unknowns, Jacobian = 200 evaluations given the residual).  (A perturbation that
+    makes neurons fire starts a wave; the event-driven map is then discontinuous in u and Newton from there is a matter
+    of luck — the oracle shows both outcomes — so that is not a test.)"""
+    nc, N, T = 100, 1024, 0.5
+    I = float(np.float32(0.9))
+    xs = np.linspace(0.0, 2.0 * np.pi, nc, endpoint=False)
+    rest = np.concatenate([np.full(nc, I), np.zeros(nc)])
+
+    def solve(guess, ndev=1):
+        sol = np.zeros(2 * nc); hist = np.full(21, np.nan); nh = C.c_int(); ms = np.zeros(1)
+        devs = (C.c_int * max(ndev, 1))(*range(max(ndev, 1)))
+        rc = host.b200_host_profile_newton(C.c_double(BETA), 2, N, nc, C.c_double(T), dp(guess), C.c_double(1e-9), 20,
+                                           C.c_double(1e-4), ndev, devs, dp(sol), dp(hist), C.byref(nh), dp(ms))
+        assert rc >= 0, host.b200_host_last_error()
+        return rc, sol, hist[:nh.value]
+
+    g = rest + np.concatenate([0.04 * np.sin(xs), 0.01 * (1 + np.cos(2 * xs))])          # max v = 0.94 < vth
+    rc, sol, hist = solve(g)
+    assert rc == 1 and len(hist) == 2 and hist[0] > 1e-2 and hist[-1] < 1e-9
+    assert np.max(np.abs(sol - rest)) < 1e-9
+    if b200.device_count() >= 2:
+        rc3, sol3, hist3 = solve(g, min(b200.device_count(), 4))
+        assert rc3 == rc and np.array_equal(sol3, sol) and np.array_equal(hist3, hist)
