@@ -581,6 +581,20 @@ def main():
                         rec["cpu_baseline"] = {"value": 1.0 / sec, "unit": "map evals/s", "cores": th, "kind": "port",
                                                "sample": f"{rs} of the 1000 realisations, scaled; oracle restatement of EventDrivenMap::ComputeF"}
                     extra[f"map_eval_R1000_N1024_sigma{sigma}"] = rec
+                # the state the reference driver ends in (Driver.cu:68-71: N = 512) and the reference's own device
+                # arithmetic (FP32): its unmodified kernels need ~7 ms per ComputeF for this on the same GPU
+                # (profiles/r2_reference_run_on_b200.txt)
+                for prec, nn in (("f64", 512), ("f32", 512), ("f32", 1024)):
+                    m = B.EventDrivenMap([BETA], 1000, noNeurons=nn, precision=prec)
+                    m.EnableTiming(True)
+                    for _ in range(3):
+                        m.ComputeF(Z_DRIVER)
+                    evs = []
+                    for _ in range(5):
+                        m.ComputeF(Z_DRIVER); evs.append(m.LastEvolveMs())
+                    extra[f"map_eval_R1000_N{nn}_{prec}"] = {"evolve_kernel_ms": float(np.mean(evs)), "events": m.LastCounters()["events"],
+                                                            "arithmetic": "FP32 (the reference's device precision)" if prec == "f32" else "FP64"}
+                    m.close()
                 # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
                 # items sharded over the ranks, positions gathered with one NCCL all-gather
                 jm = parallel.ShardedJacobian([BETA], 1000, noNeurons=1024, group=dist)
