@@ -582,8 +582,8 @@ def main():
                                                "sample": f"{rs} of the 1000 realisations, scaled; oracle restatement of EventDrivenMap::ComputeF"}
                     extra[f"map_eval_R1000_N1024_sigma{sigma}"] = rec
                 # the state the reference driver ends in (Driver.cu:68-71: N = 512) and the reference's own device
-                # arithmetic (FP32): its unmodified kernels need ~7 ms per ComputeF for this on the same GPU
-                # (profiles/r2_reference_run_on_b200.txt)
+                # arithmetic (FP32): its unmodified kernels take 14.0 ms (N = 1024) / 3.2 ms (N = 512) per ComputeF on
+                # the same GPU (tools/ref_time.py, profiles/r2_reference_time.txt)
                 for prec, nn in (("f64", 512), ("f32", 512), ("f32", 1024)):
                     m = B.EventDrivenMap([BETA], 1000, noNeurons=nn, precision=prec)
                     m.EnableTiming(True)

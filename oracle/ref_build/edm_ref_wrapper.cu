@@ -17,6 +17,7 @@
 #include "NewtonSolver.hpp"
 #include "Stability.hpp"
 #undef private
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <vector>
@@ -138,6 +139,23 @@ int edm_ref_newton(double beta, unsigned R, int N, float T, float sigma, unsigne
 /* Stability::ComputeNumUnstableEigenvalues (Stability.cpp:22-36) of the reference map at z.
  * mFiniteDifferenceEpsilon has no setter and is never initialised in the reference
  * (Stability.hpp:50); it is set here through the lifted access. */
+/* wall time of `reps` calls of the reference's own EventDrivenMap::ComputeF (after `warm` untimed ones), in ms per
+ * call; ComputeF ends with a blocking cudaMemcpy (EventDrivenMap.cu:234), so the host clock sees the device work */
+double edm_ref_time_compute_f(double beta, unsigned R, int N, float T, float sigma, unsigned long long seed,
+                              const double* z, int warm, int reps) {
+  EventDrivenMap* m = make_map(beta, R, N, T, sigma, seed);
+  arma::vec Z(noSpikes), F(noSpikes);
+  for (int i = 0; i < noSpikes; ++i) Z[i] = z[i];
+  for (int i = 0; i < warm; ++i) m->ComputeF(Z, F);
+  cudaDeviceSynchronize();
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < reps; ++i) m->ComputeF(Z, F);
+  cudaDeviceSynchronize();
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);
+  delete m;
+  return ms;
+}
+
 int edm_ref_unstable(double beta, unsigned R, int N, float T, float sigma, unsigned long long seed,
                      const double* z, double fd_epsilon) {
   EventDrivenMap* m = make_map(beta, R, N, T, sigma, seed);

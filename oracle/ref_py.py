@@ -78,3 +78,12 @@ def unstable(z, beta, R, N=1024, T=5.0, sigma=0.0, seed=42, eps=1e-2):
     fn.restype = C.c_int
     fn.argtypes = [C.c_double, C.c_uint, C.c_int, C.c_float, C.c_float, C.c_ulonglong, C.c_void_p, C.c_double]
     return fn(beta, R, N, T, sigma, seed, _p(z), eps)
+
+
+def time_compute_f(z, beta, R, N=1024, T=5.0, sigma=0.0, seed=42, warm=3, reps=10):
+    """ms per call of the reference's own ComputeF on this GPU (host clock around its blocking calls)."""
+    z = np.ascontiguousarray(z, np.float64)
+    fn = lib().edm_ref_time_compute_f
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_double, C.c_uint, C.c_int, C.c_float, C.c_float, C.c_ulonglong, C.c_void_p, C.c_int, C.c_int]
+    return fn(beta, R, N, T, sigma, seed, _p(z), warm, reps)
