@@ -595,6 +595,17 @@ def main():
                     extra[f"map_eval_R1000_N{nn}_{prec}"] = {"evolve_kernel_ms": float(np.mean(evs)), "events": m.LastCounters()["events"],
                                                             "arithmetic": "FP32 (the reference's device precision)" if prec == "f32" else "FP64"}
                     m.close()
+                if rank == 0 and n_gpus == 1 and not args.no_cpu:
+                    # the baseline beside it: the UNMODIFIED reference (oracle/_ref: its own FP32 kernels, compiled for
+                    # sm_100a where /root/reference exists) timed on this GPU — a baseline leg, never the thing shipped
+                    try:
+                        from oracle import ref_py
+                        if ref_py.available():
+                            extra["reference_own_kernels_on_this_gpu"] = {
+                                "ms_per_compute_f": {f"R1000_N{nn}": ref_py.time_compute_f(Z_DRIVER, BETA, 1000, N=nn, warm=2, reps=5) for nn in (1024, 512)},
+                                "what": "EventDrivenMap::ComputeF of the unmodified reference (EventDrivenMap.cu, FP32 device arithmetic), host clock around its blocking calls"}
+                    except Exception as e:
+                        extra["reference_own_kernels_on_this_gpu"] = {"unavailable": repr(e)[:200]}
                 # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
                 # items sharded over the ranks, positions gathered with one NCCL all-gather
                 jm = parallel.ShardedJacobian([BETA], 1000, noNeurons=1024, group=dist)
