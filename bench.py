@@ -598,12 +598,18 @@ def main():
                 if rank == 0 and n_gpus == 1 and not args.no_cpu:
                     # the baseline beside it: the UNMODIFIED reference (oracle/_ref: its own FP32 kernels, compiled for
                     # sm_100a where /root/reference exists) timed on this GPU — a baseline leg, never the thing shipped
+                    # (in a child process: the reference's error convention is exit(-1), EventDrivenMap.cu:18-54)
                     try:
-                        from oracle import ref_py
-                        if ref_py.available():
-                            extra["reference_own_kernels_on_this_gpu"] = {
-                                "ms_per_compute_f": {f"R1000_N{nn}": ref_py.time_compute_f(Z_DRIVER, BETA, 1000, N=nn, warm=2, reps=5) for nn in (1024, 512)},
-                                "what": "EventDrivenMap::ComputeF of the unmodified reference (EventDrivenMap.cu, FP32 device arithmetic), host clock around its blocking calls"}
+                        import re, subprocess
+                        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libedm_ref.so")):
+                            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_time.py")], capture_output=True,
+                                                 text=True, timeout=120)
+                            got = {f"R1000_N{m_.group(1)}": float(m_.group(2))
+                                   for m_ in re.finditer(r"R=1000 N=(\d+): ([0-9.]+) ms per ComputeF", out.stdout)}
+                            extra["reference_own_kernels_on_this_gpu"] = (
+                                {"ms_per_compute_f": got,
+                                 "what": "EventDrivenMap::ComputeF of the unmodified reference (EventDrivenMap.cu, FP32 device arithmetic), host clock around its blocking calls"}
+                                if got else {"unavailable": (out.stderr or out.stdout)[-200:]})
                     except Exception as e:
                         extra["reference_own_kernels_on_this_gpu"] = {"unavailable": repr(e)[:200]}
                 # configs[3]: finite-difference Jacobian (n+1 = 4 evaluations x 1000 realisations), work
